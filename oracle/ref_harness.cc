@@ -1,0 +1,230 @@
+/* TEST INFRASTRUCTURE — NOT PRODUCT CODE.
+ *
+ * C-ABI harness around the UNMODIFIED reference renderer. It is compiled together with
+ * /root/reference/{bvh,mesh,scene,bmp}.cc (see oracle/Makefile) into oracle/_ref/libptref*.so
+ * and is the oracle every parity test checks the CUDA path against. Only tests/,
+ * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load it.
+ *
+ * What it wraps (reference file:line):
+ *   load_scene / setup_animation_frame / get_animation_frame_count   scene.cc:135,271,720
+ *   path_trace_pixel / tonemap_pixel                                 path_tracer.hh:637,753
+ *   baseline_render's loop nest (pixel x sample, sum, /SPP, tonemap) main.cc:12-46
+ *   pcg4d / generate_uniform_random4                                 math.hh:466,475
+ *   write_bmp                                                        bmp.cc:7
+ * The loop nest of baseline_render is restated here (main.cc cannot be linked: it owns
+ * main() and puts a 31 MB float3 array on the stack at production size, main.cc:14); the
+ * per-sample function it calls is the reference's own inline path_trace_pixel.
+ */
+#include "scene.hh"
+#include "path_tracer.hh"
+#include "bmp.hh"
+
+#include <clocale>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <unistd.h>
+#include <omp.h>
+
+namespace {
+std::unique_ptr<scene> g_scene;
+}
+
+extern "C" {
+
+struct ref_config_t
+{
+    int32_t width, height, spp, max_bounces;
+    uint32_t student_id;
+    int32_t samples_per_subframe, subframe_count, framerate;
+    /* sizeof() of the PODs crossing the boundary, so the C-ABI mirrors can be checked. */
+    int32_t sz_bvh, sz_bvh_node, sz_bvh_link, sz_tlas_instance, sz_mesh;
+    int32_t sz_subframe, sz_camera, sz_light, sz_float3, sz_float4;
+};
+
+struct ref_scene_view_t
+{
+    const void* nodes;      uint64_t n_nodes;
+    const void* links;      uint64_t n_links;
+    const void* indices;    uint64_t n_indices;
+    const void* pos;
+    const void* normal;
+    const void* albedo;
+    const void* material;   uint64_t n_verts;
+    const void* instances;  uint64_t n_instances;
+    uint64_t n_static_instances;
+    const void* subframes;  uint64_t n_subframes;
+    uint64_t n_static_nodes; /* nodes before the first per-frame TLAS (= all BLAS nodes) */
+};
+
+void ref_get_config(ref_config_t* c)
+{
+    c->width = IMAGE_WIDTH;
+    c->height = IMAGE_HEIGHT;
+    c->spp = SAMPLES_PER_PIXEL;
+    c->max_bounces = MAX_BOUNCES;
+    c->student_id = STUDENT_ID;
+    c->samples_per_subframe = SAMPLES_PER_MOTION_BLUR_STEP;
+    c->subframe_count = (SAMPLES_PER_PIXEL + SAMPLES_PER_MOTION_BLUR_STEP - 1) / SAMPLES_PER_MOTION_BLUR_STEP;
+    c->framerate = FRAMERATE;
+    c->sz_bvh = sizeof(bvh);
+    c->sz_bvh_node = sizeof(bvh_node);
+    c->sz_bvh_link = sizeof(bvh_link);
+    c->sz_tlas_instance = sizeof(tlas_instance);
+    c->sz_mesh = sizeof(mesh);
+    c->sz_subframe = sizeof(subframe);
+    c->sz_camera = sizeof(camera);
+    c->sz_light = sizeof(directional_light);
+    c->sz_float3 = sizeof(float3);
+    c->sz_float4 = sizeof(float4);
+}
+
+/* `root` must contain data/*.obj (load_scene uses relative paths, scene.cc:139-182). */
+int ref_load_scene(const char* root)
+{
+    setlocale(LC_ALL, "C"); /* main.cc:63 */
+    char cwd[4096];
+    if(!getcwd(cwd, sizeof(cwd))) return 1;
+    if(chdir(root) != 0) return 2;
+    g_scene.reset(new scene(load_scene()));
+    if(chdir(cwd) != 0) return 3;
+    return 0;
+}
+
+uint32_t ref_frame_count()
+{
+    return g_scene ? get_animation_frame_count(*g_scene) : 0;
+}
+
+int ref_setup_frame(uint32_t frame)
+{
+    if(!g_scene) return 1;
+    setup_animation_frame(*g_scene, frame);
+    return 0;
+}
+
+void ref_get_view(ref_scene_view_t* v)
+{
+    const scene& s = *g_scene;
+    v->nodes = s.bvh_buf.nodes.data();       v->n_nodes = s.bvh_buf.nodes.size();
+    v->links = s.bvh_buf.links.data();       v->n_links = s.bvh_buf.links.size();
+    v->indices = s.mesh_buf.indices.data();  v->n_indices = s.mesh_buf.indices.size();
+    v->pos = s.mesh_buf.pos.data();
+    v->normal = s.mesh_buf.normal.data();
+    v->albedo = s.mesh_buf.albedo.data();
+    v->material = s.mesh_buf.material.data(); v->n_verts = s.mesh_buf.pos.size();
+    v->instances = s.instances.data();       v->n_instances = s.instances.size();
+    v->n_static_instances = s.static_instance_count;
+    v->subframes = s.subframes.data();       v->n_subframes = s.subframes.size();
+    v->n_static_nodes = s.subframes.empty() ? s.bvh_buf.nodes.size() : s.subframes[0].tlas.node_offset;
+}
+
+/* Name -> (mesh, blas) lookup, scene.hh:49. Returns 0 when found. out = {mesh(4 uint), bvh(2 uint)} */
+int ref_find_mesh(const char* name, uint32_t out[6])
+{
+    auto it = g_scene->meshes.find(name);
+    if(it == g_scene->meshes.end()) return 1;
+    memcpy(out, &it->second.first, sizeof(mesh));
+    memcpy(out + 4, &it->second.second, sizeof(bvh));
+    return 0;
+}
+
+static inline float3 trace_one(const scene& s, uint32_t x, uint32_t y, int sample_index)
+{
+    return path_trace_pixel(
+        uint2{x, y}, sample_index,
+        s.subframes.data(), s.instances.data(),
+        s.bvh_buf.nodes.data(), s.bvh_buf.links.data(),
+        s.mesh_buf.indices.data(), s.mesh_buf.pos.data(), s.mesh_buf.normal.data(),
+        s.mesh_buf.albedo.data(), s.mesh_buf.material.data());
+}
+
+void ref_trace_sample(uint32_t x, uint32_t y, int32_t sample_index, float out[3])
+{
+    float3 c = trace_one(*g_scene, x, y, sample_index);
+    out[0] = c.x; out[1] = c.y; out[2] = c.z;
+}
+
+/* baseline_render's loop nest (main.cc:16-43) over a pixel rectangle and the sample set
+ * {s_begin + k*s_stride, k < s_count}; writes the mean radiance (sum in ascending order, then
+ * one division, main.cc:24-42) as 3 floats per pixel and, if bgra != NULL, tonemap_pixel of it.
+ * The full frame at the compiled config is rect (0,0,W,H), samples (0, SPP, 1). */
+void ref_render_rect(
+    int32_t x0, int32_t y0, int32_t w, int32_t h,
+    int32_t s_begin, int32_t s_count, int32_t s_stride,
+    float* out_rgb, uint8_t* bgra, int32_t nthreads)
+{
+    const scene& s = *g_scene;
+    if(nthreads <= 0) nthreads = omp_get_max_threads();
+    #pragma omp parallel for schedule(dynamic, 16) num_threads(nthreads)
+    for(int32_t i = 0; i < w * h; ++i)
+    {
+        uint32_t x = x0 + i % w;
+        uint32_t y = y0 + i / w;
+        float3 color = {0, 0, 0};
+        for(int32_t k = 0; k < s_count; ++k)
+            color += trace_one(s, x, y, s_begin + k * s_stride);
+        color /= (float)s_count;
+        if(out_rgb)
+        {
+            out_rgb[i * 3 + 0] = color.x;
+            out_rgb[i * 3 + 1] = color.y;
+            out_rgb[i * 3 + 2] = color.z;
+        }
+        if(bgra)
+        {
+            uchar4 p = tonemap_pixel(color);
+            memcpy(bgra + 4 * (size_t)i, &p, 4);
+        }
+    }
+}
+
+void ref_tonemap(const float rgb[3], uint8_t bgra[4])
+{
+    uchar4 p = tonemap_pixel(float3{rgb[0], rgb[1], rgb[2]});
+    memcpy(bgra, &p, 4);
+}
+
+void ref_pcg4d(uint32_t state[4])
+{
+    uint4 s = {state[0], state[1], state[2], state[3]};
+    pcg4d(&s);
+    state[0] = s.x; state[1] = s.y; state[2] = s.z; state[3] = s.w;
+}
+
+void ref_rand4(uint32_t state[4], float out[4])
+{
+    uint4 s = {state[0], state[1], state[2], state[3]};
+    float4 f = generate_uniform_random4(&s);
+    state[0] = s.x; state[1] = s.y; state[2] = s.z; state[3] = s.w;
+    out[0] = f.x; out[1] = f.y; out[2] = f.z; out[3] = f.w;
+}
+
+/* Closest-hit query straight through the reference ray_query (ray_query.hh:111-290), used by
+ * the traversal parity tests: out = {thit, u, v, w, instance_id, primitive_id, back_face}. */
+void ref_trace_closest(const float o[3], const float d[3], float tmin, float tmax,
+                       uint32_t subframe_index, float out_f[4], uint32_t out_u[3])
+{
+    const scene& s = *g_scene;
+    ray_query rq = ray_query_initialize(
+        s.subframes[subframe_index].tlas, s.instances.data(),
+        s.bvh_buf.nodes.data(), s.bvh_buf.links.data(),
+        s.mesh_buf.indices.data(), s.mesh_buf.pos.data(),
+        float3{o[0], o[1], o[2]}, float3{d[0], d[1], d[2]}, tmin, tmax);
+    while(ray_query_proceed(&rq)) ray_query_confirm(&rq);
+    out_f[0] = rq.closest.thit;
+    out_f[1] = rq.closest.barycentrics.x;
+    out_f[2] = rq.closest.barycentrics.y;
+    out_f[3] = rq.closest.barycentrics.z;
+    out_u[0] = rq.closest.instance_id;
+    out_u[1] = rq.closest.primitive_id;
+    out_u[2] = rq.closest.back_face ? 1u : 0u;
+}
+
+void ref_write_bmp(const char* name, uint32_t w, uint32_t h, const uint8_t* bgra)
+{
+    write_bmp(name, w, h, 4, w * 4, bgra); /* main.cc:97-101 */
+}
+
+} /* extern "C" */
