@@ -1,0 +1,224 @@
+/* ptgpu.h — C ABI of libptgpu.so, the B200 (sm_100a) implementation of the reference's rendering
+ * hot path: baseline_render -> path_trace_pixel -> ray_query traversal -> tonemap_pixel.
+ *
+ * C99-callable, plain pointers and sizes only. Every entry point names the reference interface
+ * it replaces (file:line relative to the reference tree).
+ *
+ * Seam (reference main.cc:82-101):
+ *     setup_animation_frame(s, f);          // caller (reference scene.cc), unchanged
+ *     baseline_render(s, image);            // <- replaced by ptgpu_render_frame()
+ *     write_bmp(..., image);                // caller, unchanged (or ptgpu_render_frame_bmp)
+ *
+ * Conventions
+ *   - return 0 on success, non-zero on error; text via ptgpu_last_error(). The reference has no
+ *     error returns (it prints and exit(1)s, mesh.cc:25-41, bmp.cc:54-59).
+ *   - the context copies everything it is given; host pointers are never retained
+ *     (setup_animation_frame reallocates them every frame, scene.cc:274-277, 712-717).
+ *   - one context per GPU, one host thread per context.
+ *   - host `float3` is 16 bytes (alignas(16), math.hh:36): all vec3 arrays are passed as 16-byte
+ *     elements.
+ */
+#ifndef PTGPU_H
+#define PTGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- POD mirrors of the reference types that cross the seam (layout-identical) ------------- */
+
+typedef struct { float x, y, z, pad; } ptgpu_float3;                 /* math.hh:36  (16 B) */
+typedef struct { float x, y, z, w; } ptgpu_float4;                   /* math.hh:37  (16 B) */
+typedef struct { ptgpu_float3 r[3]; } ptgpu_mat3;                    /* math.hh:152 (48 B) */
+typedef struct { ptgpu_float4 r[4]; } ptgpu_mat4;                    /* math.hh:153 (64 B) */
+
+typedef struct { uint32_t node_count, node_offset; } ptgpu_bvh;      /* bvh.hh:35-39  (8 B) */
+typedef struct { float min_x, min_y, min_z, max_x, max_y, max_z; } ptgpu_bvh_node; /* bvh.hh:45-49 (24 B) */
+typedef struct { uint32_t accept, cancel; } ptgpu_bvh_link;          /* bvh.hh:57-67  (8 B) */
+typedef struct {                                                      /* mesh.hh:18-28 (16 B) */
+    uint32_t vertex_count, triangle_count, index_offset, base_vertex_offset;
+} ptgpu_mesh;
+typedef struct {                                                      /* bvh.hh:73-79 (160 B) */
+    ptgpu_bvh blas;          /* @0  */
+    ptgpu_mesh m;            /* @8  */
+    uint32_t pad_[2];        /* @24 (alignment of mat4) */
+    ptgpu_mat4 transform;    /* @32 */
+    ptgpu_mat4 inv_transform;/* @96 */
+} ptgpu_tlas_instance;
+typedef struct {                                                      /* scene.hh:7-18 (96 B) */
+    ptgpu_mat3 orientation;  /* @0  */
+    ptgpu_float3 position;   /* @48 */
+    float aspect_ratio;      /* @64 */
+    float inv_focal_length;  /* @68 */
+    float focal_distance;    /* @72 */
+    float aperture_angle;    /* @76 */
+    int32_t aperture_polygon;/* @80 */
+    float aperture_radius;   /* @84 */
+    uint32_t pad_[2];
+} ptgpu_camera;
+typedef struct {                                                      /* scene.hh:20-25 (48 B) */
+    ptgpu_float3 direction;
+    ptgpu_float3 color;
+    float cos_solid_angle;
+    uint32_t pad_[3];
+} ptgpu_directional_light;
+typedef struct {                                                      /* scene.hh:27-35 (160 B) */
+    ptgpu_bvh tlas;          /* @0   */
+    uint32_t pad_[2];
+    ptgpu_camera cam;        /* @16  */
+    ptgpu_directional_light light; /* @112 */
+} ptgpu_subframe;
+
+/* The compile-time constants of config.hh, made run-time so one library serves the shipped
+ * TESTING config (config.hh:14-18), production (config.hh:21-25) and test-sized renders. */
+typedef struct {
+    int32_t width;                 /* IMAGE_WIDTH   config.hh:14/21 */
+    int32_t height;                /* IMAGE_HEIGHT  config.hh:15/22 */
+    int32_t spp;                   /* SAMPLES_PER_PIXEL config.hh:16/23 */
+    int32_t max_bounces;           /* MAX_BOUNCES   config.hh:18/25 */
+    uint32_t student_id;           /* STUDENT_ID    config.hh:5 — 4th word of the RNG key */
+    int32_t samples_per_subframe;  /* SAMPLES_PER_MOTION_BLUR_STEP config.hh:29 (8) */
+} ptgpu_config;
+
+typedef struct ptgpu_ctx ptgpu_ctx;
+
+/* ---- life cycle ----------------------------------------------------------------------------- */
+
+/* Fills cfg with the shipped config.hh values (TESTING: 640x360, 256 spp, 4 bounces,
+ * STUDENT_ID 152121358, 8 samples per motion-blur step). */
+void ptgpu_default_config(ptgpu_config* cfg);
+
+/* Creates a context on CUDA device `device`. Fails (non-zero) if no sm_100 device is present:
+ * there is no CPU fallback. On failure *out is NULL and ptgpu_last_error(NULL) has the text. */
+int ptgpu_create(ptgpu_ctx** out, int device, const ptgpu_config* cfg);
+void ptgpu_destroy(ptgpu_ctx* ctx);
+const char* ptgpu_last_error(const ptgpu_ctx* ctx);
+
+/* ---- static scene: everything load_scene() produces (scene.cc:135-269) ---------------------- */
+
+/* Replaces the by-pointer hand-over of main.cc:29-37 for the data that does not change after
+ * load_scene(): all BLAS nodes/links (bvh.hh:88-92; links hold 8 direction tables per BVH at
+ * links[8*node_offset + octant*node_count + i], bvh.cc:218-226), the mesh buffers
+ * (mesh.hh:32-44) and instances[0 .. n_static) (scene.hh:55-60). Uploads once and builds the
+ * GPU traversal layout (wide BVH per BLAS + one static TLAS). n_links must be 8*n_nodes. */
+int ptgpu_upload_static(
+    ptgpu_ctx* ctx,
+    const ptgpu_bvh_node* nodes, size_t n_nodes,
+    const ptgpu_bvh_link* links, size_t n_links,
+    const uint32_t* indices, size_t n_indices,
+    const ptgpu_float3* pos, const ptgpu_float3* normal,
+    const ptgpu_float4* albedo, const ptgpu_float4* material, size_t n_verts,
+    const ptgpu_tlas_instance* instances, size_t n_static);
+
+/* ---- per frame: everything setup_animation_frame() produces (scene.cc:271-718) -------------- */
+
+/* subframes[n_subframes]         s.subframes (scene.hh:65), one per 8 samples
+ * dyn_instances[n_dyn]           s.instances[static_instance_count ..) — instance ids in TLAS
+ *                                leaves are n_static + index into this array
+ * tlas_nodes/links               s.bvh_buf.nodes/links from the first per-frame TLAS on, i.e.
+ *                                nodes + tlas_node_base and links + 8*tlas_node_base;
+ *                                subframe.tlas.node_offset is absolute (scene.cc:714)
+ * The per-subframe TLAS link tables are used to recover which dynamic instances each subframe
+ * sees (leaf payloads, scene.cc:84-88). */
+int ptgpu_set_frame(
+    ptgpu_ctx* ctx,
+    const ptgpu_subframe* subframes, size_t n_subframes,
+    const ptgpu_tlas_instance* dyn_instances, size_t n_dyn,
+    const ptgpu_bvh_node* tlas_nodes, const ptgpu_bvh_link* tlas_links,
+    size_t n_tlas_nodes, size_t tlas_node_base);
+
+/* Same without reference TLAS arrays: the caller states each subframe's dynamic range
+ * [dyn_begin[i], dyn_end[i]) into dyn_instances (what scene.cc:651-678 keeps in `entries`).
+ * subframes[i].tlas is ignored. */
+int ptgpu_set_frame_ranges(
+    ptgpu_ctx* ctx,
+    const ptgpu_subframe* subframes, size_t n_subframes,
+    const ptgpu_tlas_instance* dyn_instances, size_t n_dyn,
+    const uint32_t* dyn_begin, const uint32_t* dyn_end);
+
+/* ---- render --------------------------------------------------------------------------------- */
+
+/* baseline_render(const scene&, uchar4* image) (main.cc:12-46): all cfg.spp samples of every
+ * pixel, mean, tonemap_pixel. out_bgra: width*height*4 bytes, B,G,R,255, row 0 = top. */
+int ptgpu_render(ptgpu_ctx* ctx, uint8_t* out_bgra);
+
+/* baseline_render + write_bmp's packing (bmp.cc:15-52) fused: out_bmp receives the complete
+ * file image (54-byte header, bottom-up BGR rows padded to 4 bytes); size from ptgpu_bmp_size. */
+int ptgpu_render_bmp(ptgpu_ctx* ctx, uint8_t* out_bmp);
+size_t ptgpu_bmp_size(const ptgpu_ctx* ctx);
+
+/* ptgpu_set_frame + ptgpu_render in one call: the drop-in for main.cc:88. */
+int ptgpu_render_frame(
+    ptgpu_ctx* ctx,
+    const ptgpu_subframe* subframes, size_t n_subframes,
+    const ptgpu_tlas_instance* dyn_instances, size_t n_dyn,
+    const ptgpu_bvh_node* tlas_nodes, const ptgpu_bvh_link* tlas_links,
+    size_t n_tlas_nodes, size_t tlas_node_base,
+    uint8_t* out_bgra);
+
+/* Test hook: the loop nest of main.cc:16-43 over the pixel rectangle (x0,y0,w,h) and the sample
+ * set {s_begin + k*s_stride : k < s_count}. out_rgb (may be NULL): w*h*3 floats, mean linear
+ * radiance; out_bgra (may be NULL): w*h*4 bytes, tonemap_pixel of that mean. */
+int ptgpu_render_rect(
+    ptgpu_ctx* ctx, int32_t x0, int32_t y0, int32_t w, int32_t h,
+    int32_t s_begin, int32_t s_count, int32_t s_stride,
+    float* out_rgb, uint8_t* out_bgra);
+
+/* path_trace_pixel(xy, sample_index, ...) (path_tracer.hh:637-741) for n independent
+ * (x, y, sample_index) triples; out_rgb: n*3 floats. sample_index keeps the reference meaning:
+ * RNG key (x, y, (uint)sample_index, STUDENT_ID) and subframe sample_index/8, negative -> 0. */
+int ptgpu_trace_samples(
+    ptgpu_ctx* ctx, const uint32_t* xy, const int32_t* sample_index, size_t n, float* out_rgb);
+
+/* tonemap_pixel(float3) (path_tracer.hh:753-771) for n colours (3 floats each) -> n*4 bytes BGRA. */
+int ptgpu_tonemap(ptgpu_ctx* ctx, const float* rgb, size_t n, uint8_t* out_bgra);
+
+/* Closest-hit ray query (ray_query.hh:111-290 driven as in path_tracer.hh:342-349) for n rays
+ * against subframe `subframe`: ray = {ox,oy,oz,tmin, dx,dy,dz,tmax} (8 floats);
+ * out_f = {thit,u,v,w} (4 floats), out_u = {instance_id, primitive_id, back_face} per ray. */
+int ptgpu_trace_closest(
+    ptgpu_ctx* ctx, const float* rays, size_t n, uint32_t subframe, float* out_f, uint32_t* out_u);
+
+/* pcg4d (math.hh:466-473) applied `steps` times to n 4-word states, in place. */
+int ptgpu_pcg4d(ptgpu_ctx* ctx, uint32_t* states, size_t n, int32_t steps);
+
+/* ---- device-resident rendering for pipelined drivers and the benchmark ---------------------- */
+
+/* Launches the frame render on the context's stream and returns without waiting; the finished
+ * frame stays in device memory. ptgpu_fetch_* waits and copies it out. */
+int ptgpu_render_async(ptgpu_ctx* ctx);
+int ptgpu_fetch_bgra(ptgpu_ctx* ctx, uint8_t* out_bgra);
+int ptgpu_fetch_bmp(ptgpu_ctx* ctx, uint8_t* out_bmp);
+int ptgpu_sync(ptgpu_ctx* ctx);
+/* Device time (CUDA events on the context's stream) of the most recent finished render, in ms;
+ * `launches` (may be NULL) receives the number of kernels it launched. */
+int ptgpu_last_render_ms(ptgpu_ctx* ctx, float* ms, int32_t* launches);
+
+/* ---- options and instrumentation ------------------------------------------------------------ */
+
+/* "traversal": 0 = wide GPU BVH (default), 1 = walk the reference link tables as they are
+ *              (stackless, ray_query.hh:184-223) — the counting / cross-check mode
+ * "counters":  1 = count per-path events (rays, node visits, triangle tests, ...) on the
+ *              reference link tables; only with traversal = 1
+ * "kernel":    0 = persistent megakernel (default), 1 = simple one-thread-per-path kernel */
+int ptgpu_set_option(ptgpu_ctx* ctx, const char* key, int64_t value);
+
+enum {
+    PTGPU_CNT_PATHS = 0, PTGPU_CNT_RAYS, PTGPU_CNT_NODE_VISITS, PTGPU_CNT_TRI_TESTS,
+    PTGPU_CNT_BLAS_ENTERS, PTGPU_CNT_BOUNCES, PTGPU_CNT_SHADOW_RAYS, PTGPU_CNT_SKY_MARCHES,
+    PTGPU_CNT_SKY_ATTENUATIONS, PTGPU_CNT_HITS, PTGPU_CNT_MISSES, PTGPU_CNT_COUNT = 16
+};
+/* Reads and clears the event counters accumulated since the last call. */
+int ptgpu_read_counters(ptgpu_ctx* ctx, uint64_t out[PTGPU_CNT_COUNT]);
+
+/* Sizes of the device-side scene, for reporting: out = {static bytes, per-frame bytes,
+ * wide-BVH nodes, triangles, static instances}. */
+int ptgpu_scene_stats(ptgpu_ctx* ctx, uint64_t out[8]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PTGPU_H */

@@ -1,0 +1,11 @@
+#!/bin/sh
+# Builds libptgpu.so (CUDA kernels + C ABI) in-tree for sm_100a.
+set -e
+cd "$(dirname "$0")"
+NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
+FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xcompiler -O2 --expt-relaxed-constexpr ${PTGPU_NVCC_FLAGS}"
+mkdir -p build
+$NVCC $FLAGS -Xptxas -v -c csrc/ptgpu_api.cu -o build/ptgpu_api.o 2> build/ptxas_api.log || { cat build/ptxas_api.log; exit 1; }
+$NVCC $FLAGS -c csrc/bvh_wide.cu -o build/bvh_wide.o
+$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o libptgpu.so build/ptgpu_api.o build/bvh_wide.o -lcudart_static -lpthread -ldl -lrt
+echo "built $(pwd)/libptgpu.so"

@@ -1,0 +1,43 @@
+// Host side of the GPU acceleration layout: flattens the reference's link-table BVHs
+// (bvh.hh:35-67, built by bvh.cc:43-229) into 4-wide nodes with multi-triangle leaves and
+// pre-gathered triangle vertices, and builds one static TLAS over the static instances.
+#pragma once
+#include "../../include/ptgpu.h"
+#include "pt_scene.cuh"
+
+#include <string>
+#include <vector>
+
+namespace pt {
+
+struct WideBlasInfo
+{
+    uint32_t ref_node_offset, ref_node_count;   // the reference bvh handle this was built from
+    ptgpu_mesh mesh;                            // derived; checked against every instance using it
+    uint32_t max_stack;                         // stack entries a traversal of this BLAS can need
+};
+
+struct WideScene
+{
+    std::vector<WideNode> nodes;        // all BLASes, concatenated
+    std::vector<float4> tris;           // 3 per triangle slot
+    std::vector<WideBlas> blas;
+    std::vector<WideBlasInfo> blas_info;
+    std::vector<WideInstance> instances; // static instances
+    std::vector<WideNode> tlas;         // static TLAS
+    uint32_t max_stack = 0;             // worst case over TLAS + any BLAS (+1 for the exit marker)
+};
+
+constexpr int WIDE_LEAF_MAX = 4;        // triangles per leaf
+constexpr int WIDE_STACK = 96;          // traversal stack entries (pt_wide.cuh)
+
+bool build_wide_scene(
+    const ptgpu_bvh_node* nodes, size_t n_nodes, const ptgpu_bvh_link* links,
+    const uint32_t* indices, size_t n_indices, const ptgpu_float3* pos, size_t n_verts,
+    const ptgpu_tlas_instance* instances, size_t n_static,
+    WideScene& out, std::string& err);
+
+// Fills the traversal record of one instance (static or per-frame). False if its BLAS is unknown.
+bool make_wide_instance(const WideScene& ws, const ptgpu_tlas_instance& inst, uint32_t ref_index, WideInstance& out);
+
+} // namespace pt

@@ -1,0 +1,730 @@
+// C ABI of libptgpu.so (include/ptgpu.h): context, device memory, uploads, launches.
+#include "../../include/ptgpu.h"
+#include "pt_kernels.cuh"
+#include "pt_wide.cuh"
+#include "pt_mega.cuh"
+#include "bvh_wide.hh"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+static_assert(sizeof(ptgpu_tlas_instance) == 160, "tlas_instance must be 160 B (bvh.hh:73-79)");
+static_assert(sizeof(ptgpu_subframe) == 160, "subframe must be 160 B (scene.hh:27-35)");
+static_assert(sizeof(ptgpu_camera) == 96, "camera must be 96 B (scene.hh:7-18)");
+static_assert(sizeof(ptgpu_directional_light) == 48, "directional_light must be 48 B (scene.hh:20-25)");
+static_assert(sizeof(ptgpu_bvh_node) == 24 && sizeof(ptgpu_bvh_link) == 8 && sizeof(ptgpu_mesh) == 16, "bvh PODs");
+static_assert(offsetof(ptgpu_tlas_instance, transform) == 32 && offsetof(ptgpu_tlas_instance, inv_transform) == 96, "instance offsets");
+static_assert(offsetof(ptgpu_subframe, cam) == 16 && offsetof(ptgpu_subframe, light) == 112, "subframe offsets");
+
+using namespace pt;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+template<class T>
+struct DevBuf
+{
+    T* p = nullptr;
+    size_t cap = 0; // elements
+    cudaError_t reserve(size_t n)
+    {
+        if(n <= cap) return cudaSuccess;
+        if(p) cudaFree(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMalloc(&p, n * sizeof(T));
+        if(e == cudaSuccess) cap = n;
+        return e;
+    }
+    void release() { if(p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+} // namespace
+
+struct ptgpu_ctx
+{
+    int device = 0;
+    ptgpu_config cfg{};
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+    std::string error;
+    int sm_count = 0;
+
+    // options
+    int traversal = 0; // 0 wide, 1 links
+    int counters_on = 0;
+    int kernel = 0;    // 0 megakernel, 1 simple tiles
+
+    // static scene, reference layout
+    DevBuf<float2> ref_nodes;     // 3 per node; static region then per-frame TLAS region
+    DevBuf<uint2> ref_links;
+    DevBuf<uint32_t> indices;
+    DevBuf<float4> pos, normal, albedo, material;
+    DevBuf<RefInstance> instances; // static + dynamic
+    size_t n_static_nodes = 0, n_static = 0, n_verts = 0, n_indices = 0;
+    bool have_static = false;
+    std::vector<ptgpu_tlas_instance> host_static; // kept for the wide instance records
+
+    // wide layout
+    WideScene wide_host;            // host-side build result (node/tri arrays, blas table)
+    DevBuf<WideNode> wnodes;
+    DevBuf<float4> wtris;
+    DevBuf<WideBlas> wblas;
+    DevBuf<WideInstance> winst;     // static + dynamic
+    DevBuf<WideNode> wtlas;
+    size_t n_wtlas = 0;
+
+    // per frame
+    DevBuf<RefSubframe> subframes;
+    DevBuf<uint2> dyn_range;
+    size_t n_subframes = 0, n_dyn = 0;
+    bool have_frame = false, frame_has_ref_tlas = false;
+    std::vector<uint8_t> staging;   // pinned-size-agnostic host staging for per-frame uploads
+    void* pinned = nullptr; size_t pinned_cap = 0;
+
+    // outputs
+    DevBuf<uchar4> out_bgra;
+    DevBuf<uint8_t> out_bmp;
+    DevBuf<float> out_rgb;
+    DevBuf<Counters> counters;
+    DevBuf<MegaState> mega_state;
+    uint32_t bmp_pitch = 0;
+    bool bmp_header_done = false;
+    bool render_pending = false;
+    int last_launches = 0;
+
+    // scratch for the small utility entry points
+    DevBuf<uint8_t> scratch_a, scratch_b, scratch_c;
+};
+
+namespace {
+
+int fail(ptgpu_ctx* c, const char* fmt, ...)
+{
+    char buf[1024];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof(buf), fmt, ap); va_end(ap);
+    if(c) c->error = buf; else g_create_error = buf;
+    return 1;
+}
+
+#define CK(call) do { cudaError_t e_ = (call); if(e_ != cudaSuccess) \
+    return fail(ctx, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while(0)
+
+int use(ptgpu_ctx* ctx)
+{
+    CK(cudaSetDevice(ctx->device));
+    return 0;
+}
+
+void* pinned_staging(ptgpu_ctx* ctx, size_t bytes)
+{
+    if(bytes > ctx->pinned_cap)
+    {
+        if(ctx->pinned) cudaFreeHost(ctx->pinned);
+        ctx->pinned = nullptr; ctx->pinned_cap = 0;
+        size_t cap = bytes + bytes / 2 + 4096;
+        if(cudaMallocHost(&ctx->pinned, cap) != cudaSuccess) return nullptr;
+        ctx->pinned_cap = cap;
+    }
+    return ctx->pinned;
+}
+
+Scene make_scene(ptgpu_ctx* ctx)
+{
+    Scene s{};
+    s.ref_nodes = ctx->ref_nodes.p;
+    s.ref_links = ctx->ref_links.p;
+    s.indices = ctx->indices.p;
+    s.pos = ctx->pos.p; s.normal = ctx->normal.p; s.albedo = ctx->albedo.p; s.material = ctx->material.p;
+    s.instances = ctx->instances.p;
+    s.subframes = ctx->subframes.p;
+    s.wnodes = ctx->wnodes.p; s.wtris = ctx->wtris.p; s.wblas = ctx->wblas.p; s.winst = ctx->winst.p;
+    s.wtlas = ctx->wtlas.p; s.dyn_range = ctx->dyn_range.p;
+    s.n_static = (uint32_t)ctx->n_static;
+    s.n_subframes = (uint32_t)ctx->n_subframes;
+    s.width = ctx->cfg.width; s.height = ctx->cfg.height;
+    s.max_bounces = ctx->cfg.max_bounces;
+    s.samples_per_subframe = ctx->cfg.samples_per_subframe;
+    s.student_id = ctx->cfg.student_id;
+    return s;
+}
+
+int check_ready(ptgpu_ctx* ctx)
+{
+    if(!ctx) return 1;
+    if(!ctx->have_static) return fail(ctx, "ptgpu_upload_static has not been called");
+    if(!ctx->have_frame) return fail(ctx, "ptgpu_set_frame has not been called");
+    if(ctx->traversal == 1 && !ctx->frame_has_ref_tlas)
+        return fail(ctx, "traversal=links needs the reference TLAS arrays (use ptgpu_set_frame, not _ranges)");
+    return 0;
+}
+
+// Launch one render job on the context's stream. Returns kernels launched, or -1.
+int launch_job(ptgpu_ctx* ctx, const RenderJob& job)
+{
+    Scene sc = make_scene(ctx);
+    int launches = 0;
+    if(ctx->traversal == 1)
+    {
+        const int tiles = ((job.w + TILE_W - 1) / TILE_W) * ((job.h + TILE_H - 1) / TILE_H);
+        if(ctx->counters_on)
+            render_tiles_kernel<LinksTrav<true>, true><<<tiles, TILE_THREADS, 0, ctx->stream>>>(sc, job, ctx->counters.p);
+        else
+            render_tiles_kernel<LinksTrav<false>, false><<<tiles, TILE_THREADS, 0, ctx->stream>>>(sc, job, nullptr);
+        launches = 1;
+    }
+    else if(ctx->kernel == 1)
+    {
+        const int tiles = ((job.w + TILE_W - 1) / TILE_W) * ((job.h + TILE_H - 1) / TILE_H);
+        render_tiles_kernel<WideTrav, false><<<tiles, TILE_THREADS, 0, ctx->stream>>>(sc, job, nullptr);
+        launches = 1;
+    }
+    else
+    {
+        launches = launch_mega(sc, job, ctx->mega_state.p, ctx->sm_count, ctx->stream);
+    }
+    if(cudaGetLastError() != cudaSuccess) return -1;
+    return launches;
+}
+
+int upload_frame_common(ptgpu_ctx* ctx, const ptgpu_subframe* subframes, size_t n_subframes,
+                        const ptgpu_tlas_instance* dyn, size_t n_dyn, const std::vector<uint2>& ranges)
+{
+    // one pinned staging block, three async copies, all on the render stream
+    const size_t sz_sub = n_subframes * sizeof(RefSubframe);
+    const size_t sz_dyn = n_dyn * sizeof(RefInstance);
+    const size_t sz_rng = n_subframes * sizeof(uint2);
+    const size_t sz_win = n_dyn * sizeof(WideInstance);
+    // the previous frame's copies must have left the staging block
+    CK(cudaStreamSynchronize(ctx->stream));
+    uint8_t* st = (uint8_t*)pinned_staging(ctx, sz_sub + sz_dyn + sz_rng + sz_win + 64);
+    if(!st) return fail(ctx, "pinned staging allocation failed");
+    CK(ctx->subframes.reserve(n_subframes));
+    CK(ctx->dyn_range.reserve(n_subframes));
+    if(ctx->instances.cap < ctx->n_static + n_dyn)
+    {   // grow, keeping the static part
+        DevBuf<RefInstance> nb; CK(nb.reserve(ctx->n_static + n_dyn + 64));
+        CK(cudaMemcpyAsync(nb.p, ctx->instances.p, ctx->n_static * sizeof(RefInstance), cudaMemcpyDeviceToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        ctx->instances.release(); ctx->instances = nb;
+        DevBuf<WideInstance> wb; CK(wb.reserve(ctx->n_static + n_dyn + 64));
+        CK(cudaMemcpyAsync(wb.p, ctx->winst.p, ctx->n_static * sizeof(WideInstance), cudaMemcpyDeviceToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        ctx->winst.release(); ctx->winst = wb;
+    }
+    size_t off = 0;
+    memcpy(st + off, subframes, sz_sub);
+    CK(cudaMemcpyAsync(ctx->subframes.p, st + off, sz_sub, cudaMemcpyHostToDevice, ctx->stream));
+    off += sz_sub;
+    if(n_dyn)
+    {
+        memcpy(st + off, dyn, sz_dyn);
+        CK(cudaMemcpyAsync(ctx->instances.p + ctx->n_static, st + off, sz_dyn, cudaMemcpyHostToDevice, ctx->stream));
+        off += sz_dyn;
+        WideInstance* wi = (WideInstance*)(st + ((off + 15) & ~size_t(15)));
+        for(size_t i = 0; i < n_dyn; ++i)
+            if(!make_wide_instance(ctx->wide_host, dyn[i], (uint32_t)(ctx->n_static + i), wi[i]))
+                return fail(ctx, "dynamic instance %zu references an unknown BLAS (node_offset %u)", i, dyn[i].blas.node_offset);
+        CK(cudaMemcpyAsync(ctx->winst.p + ctx->n_static, wi, sz_win, cudaMemcpyHostToDevice, ctx->stream));
+        off = ((off + 15) & ~size_t(15)) + sz_win;
+    }
+    memcpy(st + off, ranges.data(), sz_rng);
+    CK(cudaMemcpyAsync(ctx->dyn_range.p, st + off, sz_rng, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->n_subframes = n_subframes;
+    ctx->n_dyn = n_dyn;
+    ctx->have_frame = true;
+    return 0;
+}
+
+} // namespace
+
+extern "C" {
+
+void ptgpu_default_config(ptgpu_config* cfg)
+{
+    cfg->width = 640; cfg->height = 360; cfg->spp = 256; cfg->max_bounces = 4;
+    cfg->student_id = 152121358u; cfg->samples_per_subframe = 8;
+}
+
+int ptgpu_create(ptgpu_ctx** out, int device, const ptgpu_config* cfg)
+{
+    if(!out) return 1;
+    *out = nullptr;
+    ptgpu_ctx* ctx = nullptr; // for CK's fail()
+    if(!cfg || cfg->width <= 0 || cfg->height <= 0 || cfg->spp <= 0 || cfg->max_bounces < 0 || cfg->samples_per_subframe <= 0)
+        return fail(nullptr, "invalid ptgpu_config");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if(e != cudaSuccess || n == 0)
+        return fail(nullptr, "no CUDA device: %s (libptgpu has no CPU fallback)", cudaGetErrorString(e));
+    if(device < 0 || device >= n) return fail(nullptr, "device %d out of range (have %d)", device, n);
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if(prop.major != 10)
+        return fail(nullptr, "device %d is sm_%d%d; libptgpu is built for sm_100a only", device, prop.major, prop.minor);
+    CK(cudaSetDevice(device));
+    ctx = new ptgpu_ctx();
+    ctx->device = device;
+    ctx->cfg = *cfg;
+    ctx->sm_count = prop.multiProcessorCount;
+    cudaError_t e1 = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    cudaError_t e2 = cudaEventCreate(&ctx->ev_begin);
+    cudaError_t e3 = cudaEventCreate(&ctx->ev_end);
+    if(e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess)
+    {
+        delete ctx;
+        return fail(nullptr, "stream/event creation failed");
+    }
+    ctx->bmp_pitch = ((uint32_t)cfg->width * 3u + 3u) / 4u * 4u;
+    const size_t npix = (size_t)cfg->width * cfg->height;
+    if(ctx->out_bgra.reserve(npix) != cudaSuccess || ctx->out_bmp.reserve(54 + (size_t)ctx->bmp_pitch * cfg->height) != cudaSuccess ||
+       ctx->counters.reserve(1) != cudaSuccess || ctx->mega_state.reserve(1) != cudaSuccess)
+    {
+        delete ctx;
+        return fail(nullptr, "output allocation failed");
+    }
+    cudaMemset(ctx->out_bmp.p, 0, 54 + (size_t)ctx->bmp_pitch * cfg->height);
+    cudaMemset(ctx->counters.p, 0, sizeof(Counters));
+    cudaMemset(ctx->mega_state.p, 0, sizeof(MegaState));
+    *out = ctx;
+    return 0;
+}
+
+void ptgpu_destroy(ptgpu_ctx* ctx)
+{
+    if(!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    ctx->ref_nodes.release(); ctx->ref_links.release(); ctx->indices.release();
+    ctx->pos.release(); ctx->normal.release(); ctx->albedo.release(); ctx->material.release();
+    ctx->instances.release(); ctx->wnodes.release(); ctx->wtris.release(); ctx->wblas.release();
+    ctx->winst.release(); ctx->wtlas.release(); ctx->subframes.release(); ctx->dyn_range.release();
+    ctx->out_bgra.release(); ctx->out_bmp.release(); ctx->out_rgb.release(); ctx->counters.release();
+    ctx->mega_state.release();
+    ctx->scratch_a.release(); ctx->scratch_b.release(); ctx->scratch_c.release();
+    if(ctx->pinned) cudaFreeHost(ctx->pinned);
+    cudaEventDestroy(ctx->ev_begin); cudaEventDestroy(ctx->ev_end);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char* ptgpu_last_error(const ptgpu_ctx* ctx)
+{
+    return ctx ? ctx->error.c_str() : g_create_error.c_str();
+}
+
+int ptgpu_upload_static(
+    ptgpu_ctx* ctx,
+    const ptgpu_bvh_node* nodes, size_t n_nodes,
+    const ptgpu_bvh_link* links, size_t n_links,
+    const uint32_t* indices, size_t n_indices,
+    const ptgpu_float3* pos, const ptgpu_float3* normal,
+    const ptgpu_float4* albedo, const ptgpu_float4* material, size_t n_verts,
+    const ptgpu_tlas_instance* instances, size_t n_static)
+{
+    if(!ctx) return 1;
+    if(!nodes || !links || !indices || !pos || !normal || !albedo || !material || !instances)
+        return fail(ctx, "ptgpu_upload_static: null array");
+    if(n_links != 8 * n_nodes) return fail(ctx, "ptgpu_upload_static: n_links (%zu) must be 8*n_nodes (%zu)", n_links, n_nodes);
+    if(n_static == 0 || n_nodes == 0) return fail(ctx, "ptgpu_upload_static: empty scene");
+    if(use(ctx)) return 1;
+
+    // reference layout, with head-room after the static region for the per-frame TLAS (links mode)
+    CK(ctx->ref_nodes.reserve(3 * n_nodes));
+    CK(ctx->ref_links.reserve(n_links));
+    CK(ctx->indices.reserve(n_indices));
+    CK(ctx->pos.reserve(n_verts)); CK(ctx->normal.reserve(n_verts));
+    CK(ctx->albedo.reserve(n_verts)); CK(ctx->material.reserve(n_verts));
+    CK(ctx->instances.reserve(n_static + 64));
+    CK(cudaMemcpy(ctx->ref_nodes.p, nodes, n_nodes * sizeof(ptgpu_bvh_node), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->ref_links.p, links, n_links * sizeof(ptgpu_bvh_link), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->indices.p, indices, n_indices * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->pos.p, pos, n_verts * 16, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->normal.p, normal, n_verts * 16, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->albedo.p, albedo, n_verts * 16, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->material.p, material, n_verts * 16, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->instances.p, instances, n_static * sizeof(RefInstance), cudaMemcpyHostToDevice));
+    ctx->n_static_nodes = n_nodes; ctx->n_static = n_static; ctx->n_verts = n_verts; ctx->n_indices = n_indices;
+    ctx->host_static.assign(instances, instances + n_static);
+
+    // GPU traversal layout: a wide BVH per distinct BLAS + one static TLAS
+    std::string err;
+    if(!build_wide_scene(nodes, n_nodes, links, indices, n_indices, pos, n_verts, instances, n_static, ctx->wide_host, err))
+        return fail(ctx, "wide BVH build failed: %s", err.c_str());
+    const WideScene& w = ctx->wide_host;
+    CK(ctx->wnodes.reserve(w.nodes.size()));
+    CK(ctx->wtris.reserve(w.tris.size()));
+    CK(ctx->wblas.reserve(w.blas.size()));
+    CK(ctx->winst.reserve(n_static + 64));
+    CK(ctx->wtlas.reserve(w.tlas.size()));
+    CK(cudaMemcpy(ctx->wnodes.p, w.nodes.data(), w.nodes.size() * sizeof(WideNode), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->wtris.p, w.tris.data(), w.tris.size() * sizeof(float4), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->wblas.p, w.blas.data(), w.blas.size() * sizeof(WideBlas), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->winst.p, w.instances.data(), n_static * sizeof(WideInstance), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->wtlas.p, w.tlas.data(), w.tlas.size() * sizeof(WideNode), cudaMemcpyHostToDevice));
+    ctx->n_wtlas = w.tlas.size();
+    ctx->have_static = true;
+    ctx->have_frame = false;
+    return 0;
+}
+
+int ptgpu_set_frame(
+    ptgpu_ctx* ctx,
+    const ptgpu_subframe* subframes, size_t n_subframes,
+    const ptgpu_tlas_instance* dyn_instances, size_t n_dyn,
+    const ptgpu_bvh_node* tlas_nodes, const ptgpu_bvh_link* tlas_links,
+    size_t n_tlas_nodes, size_t tlas_node_base)
+{
+    if(!ctx) return 1;
+    if(!ctx->have_static) return fail(ctx, "ptgpu_set_frame before ptgpu_upload_static");
+    if(!subframes || n_subframes == 0) return fail(ctx, "ptgpu_set_frame: no subframes");
+    if(!tlas_nodes || !tlas_links) return fail(ctx, "ptgpu_set_frame: null TLAS arrays");
+    if(tlas_node_base != ctx->n_static_nodes)
+        return fail(ctx, "ptgpu_set_frame: tlas_node_base %zu != static node count %zu", tlas_node_base, ctx->n_static_nodes);
+    if(use(ctx)) return 1;
+
+    // Which dynamic instances does each subframe see? Read the leaf payloads of its TLAS
+    // (octant-0 link table; all eight tables hold the same leaves, bvh.cc:170-193). The set is
+    // [n_static, static_end) U [dyn_begin, dyn_end) (scene.cc:75-91, 634-674): a prefix shared by
+    // all subframes (logo, buddha) plus one contiguous per-subframe range.
+    std::vector<uint8_t> seen;
+    std::vector<uint2> final_ranges(n_subframes);
+    for(size_t i = 0; i < n_subframes; ++i)
+    {
+        const ptgpu_bvh& t = subframes[i].tlas;
+        if(t.node_offset < tlas_node_base || (size_t)t.node_offset + t.node_count > tlas_node_base + n_tlas_nodes)
+            return fail(ctx, "ptgpu_set_frame: subframe %zu TLAS [%u,+%u) outside the passed arrays", i, t.node_offset, t.node_count);
+        const ptgpu_bvh_link* l = tlas_links + 8 * (size_t)(t.node_offset - tlas_node_base);
+        seen.assign(n_dyn, 0);
+        size_t n_static_seen = 0;
+        for(uint32_t k = 0; k < t.node_count; ++k)
+        {
+            if(!(l[k].accept & 0x80000000u)) continue;
+            const uint32_t id = l[k].accept & 0x7FFFFFFFu;
+            if(id < ctx->n_static) { n_static_seen++; continue; }
+            if(id >= ctx->n_static + n_dyn) return fail(ctx, "ptgpu_set_frame: TLAS leaf %u beyond the instance array", id);
+            seen[id - ctx->n_static] = 1;
+        }
+        if(n_static_seen != ctx->n_static)
+            return fail(ctx, "ptgpu_set_frame: subframe %zu TLAS holds %zu of %zu static instances", i, n_static_seen, ctx->n_static);
+        uint32_t p = 0; while(p < n_dyn && seen[p]) ++p;
+        uint32_t a = p; while(a < n_dyn && !seen[a]) ++a;
+        uint32_t b = a; while(b < n_dyn && seen[b]) ++b;
+        for(uint32_t k = b; k < n_dyn; ++k)
+            if(seen[k]) return fail(ctx, "ptgpu_set_frame: subframe %zu dynamic set is not prefix + one range", i);
+        if(a == n_dyn) { a = b = p; }
+        // kernel encoding: x = prefix length p (ids n_static .. n_static+p), y = a | (b-a) << 20
+        if(a >= (1u << 20) || (b - a) >= (1u << 12)) return fail(ctx, "ptgpu_set_frame: too many dynamic instances");
+        final_ranges[i] = make_uint2(p, a | ((b - a) << 20));
+    }
+    if(upload_frame_common(ctx, subframes, n_subframes, dyn_instances, n_dyn, final_ranges)) return 1;
+
+    if(ctx->traversal == 1)
+    {   // links mode also needs the reference TLAS behind the static region
+        const size_t need_nodes = ctx->n_static_nodes + n_tlas_nodes;
+        if(ctx->ref_nodes.cap < 3 * need_nodes)
+        {
+            DevBuf<float2> nb; CK(nb.reserve(3 * (need_nodes + need_nodes / 64)));
+            CK(cudaMemcpy(nb.p, ctx->ref_nodes.p, ctx->n_static_nodes * 24, cudaMemcpyDeviceToDevice));
+            ctx->ref_nodes.release(); ctx->ref_nodes = nb;
+            DevBuf<uint2> lb; CK(lb.reserve(8 * (need_nodes + need_nodes / 64)));
+            CK(cudaMemcpy(lb.p, ctx->ref_links.p, ctx->n_static_nodes * 64, cudaMemcpyDeviceToDevice));
+            ctx->ref_links.release(); ctx->ref_links = lb;
+        }
+        CK(cudaMemcpyAsync(ctx->ref_nodes.p + 3 * ctx->n_static_nodes, tlas_nodes, n_tlas_nodes * 24, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->ref_links.p + 8 * ctx->n_static_nodes, tlas_links, n_tlas_nodes * 64, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        ctx->frame_has_ref_tlas = true;
+    }
+    else ctx->frame_has_ref_tlas = false;
+    return 0;
+}
+
+int ptgpu_set_frame_ranges(
+    ptgpu_ctx* ctx,
+    const ptgpu_subframe* subframes, size_t n_subframes,
+    const ptgpu_tlas_instance* dyn_instances, size_t n_dyn,
+    const uint32_t* dyn_begin, const uint32_t* dyn_end)
+{
+    if(!ctx) return 1;
+    if(!ctx->have_static) return fail(ctx, "ptgpu_set_frame_ranges before ptgpu_upload_static");
+    if(!subframes || n_subframes == 0 || !dyn_begin || !dyn_end) return fail(ctx, "ptgpu_set_frame_ranges: null argument");
+    if(use(ctx)) return 1;
+    // shared prefix = instances before the first subframe's range (frame-static extras)
+    uint32_t prefix = n_dyn ? 0xFFFFFFFFu : 0;
+    for(size_t i = 0; i < n_subframes; ++i)
+    {
+        if(dyn_begin[i] > dyn_end[i] || dyn_end[i] > n_dyn) return fail(ctx, "ptgpu_set_frame_ranges: bad range %zu", i);
+        if(dyn_begin[i] < prefix) prefix = dyn_begin[i];
+    }
+    std::vector<uint2> ranges(n_subframes);
+    for(size_t i = 0; i < n_subframes; ++i)
+    {
+        uint32_t a = dyn_begin[i], b = dyn_end[i];
+        if(a >= (1u << 20) || (b - a) >= (1u << 12)) return fail(ctx, "ptgpu_set_frame_ranges: too many dynamic instances");
+        ranges[i] = make_uint2(prefix, a | ((b - a) << 20));
+    }
+    ctx->frame_has_ref_tlas = false;
+    return upload_frame_common(ctx, subframes, n_subframes, dyn_instances, n_dyn, ranges);
+}
+
+static int render_full(ptgpu_ctx* ctx, bool bgra, bool bmp)
+{
+    if(check_ready(ctx)) return 1;
+    if(use(ctx)) return 1;
+    if((size_t)ctx->cfg.spp > ctx->n_subframes * (size_t)ctx->cfg.samples_per_subframe)
+        return fail(ctx, "frame has %zu subframes, %d spp needs %d", ctx->n_subframes, ctx->cfg.spp,
+                    (ctx->cfg.spp + ctx->cfg.samples_per_subframe - 1) / ctx->cfg.samples_per_subframe);
+    RenderJob job{};
+    job.x0 = 0; job.y0 = 0; job.w = ctx->cfg.width; job.h = ctx->cfg.height;
+    job.s_begin = 0; job.s_count = ctx->cfg.spp; job.s_stride = 1;
+    job.out_rgb = nullptr;
+    job.out_bgra = bgra ? ctx->out_bgra.p : nullptr;
+    job.out_bmp = bmp ? ctx->out_bmp.p : nullptr;
+    job.bmp_pitch = ctx->bmp_pitch;
+    int launches = 0;
+    CK(cudaEventRecord(ctx->ev_begin, ctx->stream));
+    if(bmp && !ctx->bmp_header_done)
+    {
+        bmp_header_kernel<<<1, 32, 0, ctx->stream>>>(ctx->out_bmp.p, (uint32_t)job.w, (uint32_t)job.h, ctx->bmp_pitch);
+        ctx->bmp_header_done = true;
+        launches++;
+    }
+    int l = launch_job(ctx, job);
+    if(l < 0) return fail(ctx, "kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    launches += l;
+    CK(cudaEventRecord(ctx->ev_end, ctx->stream));
+    ctx->last_launches = launches;
+    ctx->render_pending = true;
+    return 0;
+}
+
+int ptgpu_render_async(ptgpu_ctx* ctx) { return render_full(ctx, true, true); }
+
+int ptgpu_sync(ptgpu_ctx* ctx)
+{
+    if(!ctx) return 1;
+    if(use(ctx)) return 1;
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int ptgpu_fetch_bgra(ptgpu_ctx* ctx, uint8_t* out_bgra)
+{
+    if(!ctx || !out_bgra) return 1;
+    if(use(ctx)) return 1;
+    CK(cudaMemcpyAsync(out_bgra, ctx->out_bgra.p, (size_t)ctx->cfg.width * ctx->cfg.height * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+size_t ptgpu_bmp_size(const ptgpu_ctx* ctx)
+{
+    return ctx ? 54 + (size_t)ctx->bmp_pitch * ctx->cfg.height : 0;
+}
+
+int ptgpu_fetch_bmp(ptgpu_ctx* ctx, uint8_t* out_bmp)
+{
+    if(!ctx || !out_bmp) return 1;
+    if(use(ctx)) return 1;
+    CK(cudaMemcpyAsync(out_bmp, ctx->out_bmp.p, ptgpu_bmp_size(ctx), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int ptgpu_render(ptgpu_ctx* ctx, uint8_t* out_bgra)
+{
+    if(!out_bgra) return fail(ctx, "ptgpu_render: null output");
+    if(render_full(ctx, true, false)) return 1;
+    return ptgpu_fetch_bgra(ctx, out_bgra);
+}
+
+int ptgpu_render_bmp(ptgpu_ctx* ctx, uint8_t* out_bmp)
+{
+    if(!out_bmp) return fail(ctx, "ptgpu_render_bmp: null output");
+    if(render_full(ctx, false, true)) return 1;
+    return ptgpu_fetch_bmp(ctx, out_bmp);
+}
+
+int ptgpu_render_frame(
+    ptgpu_ctx* ctx,
+    const ptgpu_subframe* subframes, size_t n_subframes,
+    const ptgpu_tlas_instance* dyn_instances, size_t n_dyn,
+    const ptgpu_bvh_node* tlas_nodes, const ptgpu_bvh_link* tlas_links,
+    size_t n_tlas_nodes, size_t tlas_node_base,
+    uint8_t* out_bgra)
+{
+    if(ptgpu_set_frame(ctx, subframes, n_subframes, dyn_instances, n_dyn, tlas_nodes, tlas_links, n_tlas_nodes, tlas_node_base)) return 1;
+    return ptgpu_render(ctx, out_bgra);
+}
+
+int ptgpu_last_render_ms(ptgpu_ctx* ctx, float* ms, int32_t* launches)
+{
+    if(!ctx || !ms) return 1;
+    if(use(ctx)) return 1;
+    if(!ctx->render_pending) return fail(ctx, "no render to time");
+    CK(cudaEventSynchronize(ctx->ev_end));
+    CK(cudaEventElapsedTime(ms, ctx->ev_begin, ctx->ev_end));
+    if(launches) *launches = ctx->last_launches;
+    return 0;
+}
+
+int ptgpu_render_rect(
+    ptgpu_ctx* ctx, int32_t x0, int32_t y0, int32_t w, int32_t h,
+    int32_t s_begin, int32_t s_count, int32_t s_stride,
+    float* out_rgb, uint8_t* out_bgra)
+{
+    if(check_ready(ctx)) return 1;
+    if(w <= 0 || h <= 0 || s_count <= 0) return fail(ctx, "ptgpu_render_rect: empty job");
+    if(x0 < 0 || y0 < 0) return fail(ctx, "ptgpu_render_rect: negative origin");
+    const long last = (long)s_begin + (long)(s_count - 1) * s_stride;
+    const long lo = s_stride >= 0 ? s_begin : last, hi = s_stride >= 0 ? last : s_begin;
+    if(hi >= 0 && (size_t)(hi / ctx->cfg.samples_per_subframe) >= ctx->n_subframes)
+        return fail(ctx, "ptgpu_render_rect: sample %ld needs subframe %ld of %zu", hi, hi / ctx->cfg.samples_per_subframe, ctx->n_subframes);
+    (void)lo;
+    if(use(ctx)) return 1;
+    const size_t npix = (size_t)w * h;
+    CK(ctx->out_rgb.reserve(npix * 3));
+    DevBuf<uchar4> tmp_bgra;
+    uchar4* d_bgra = nullptr;
+    if(out_bgra)
+    {
+        if(npix <= ctx->out_bgra.cap) d_bgra = ctx->out_bgra.p;
+        else { CK(tmp_bgra.reserve(npix)); d_bgra = tmp_bgra.p; }
+    }
+    RenderJob job{};
+    job.x0 = x0; job.y0 = y0; job.w = w; job.h = h;
+    job.s_begin = s_begin; job.s_count = s_count; job.s_stride = s_stride;
+    job.out_rgb = ctx->out_rgb.p; job.out_bgra = d_bgra; job.out_bmp = nullptr; job.bmp_pitch = 0;
+    CK(cudaEventRecord(ctx->ev_begin, ctx->stream));
+    int l = launch_job(ctx, job);
+    if(l < 0) { tmp_bgra.release(); return fail(ctx, "kernel launch failed: %s", cudaGetErrorString(cudaGetLastError())); }
+    CK(cudaEventRecord(ctx->ev_end, ctx->stream));
+    ctx->last_launches = l; ctx->render_pending = true;
+    if(out_rgb) CK(cudaMemcpyAsync(out_rgb, ctx->out_rgb.p, npix * 12, cudaMemcpyDeviceToHost, ctx->stream));
+    if(out_bgra) CK(cudaMemcpyAsync(out_bgra, d_bgra, npix * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    tmp_bgra.release();
+    if(e != cudaSuccess) return fail(ctx, "render failed: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+int ptgpu_trace_samples(ptgpu_ctx* ctx, const uint32_t* xy, const int32_t* sample_index, size_t n, float* out_rgb)
+{
+    if(check_ready(ctx)) return 1;
+    if(n == 0) return 0;
+    if(!xy || !sample_index || !out_rgb) return fail(ctx, "ptgpu_trace_samples: null argument");
+    for(size_t i = 0; i < n; ++i)
+        if(sample_index[i] >= 0 && (size_t)(sample_index[i] / ctx->cfg.samples_per_subframe) >= ctx->n_subframes)
+            return fail(ctx, "ptgpu_trace_samples: sample %d beyond the frame's subframes", sample_index[i]);
+    if(use(ctx)) return 1;
+    CK(ctx->scratch_a.reserve(n * 8)); CK(ctx->scratch_b.reserve(n * 4)); CK(ctx->scratch_c.reserve(n * 12));
+    CK(cudaMemcpyAsync(ctx->scratch_a.p, xy, n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->scratch_b.p, sample_index, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    Scene sc = make_scene(ctx);
+    const int threads = 128; const int blocks = (int)((n + threads - 1) / threads);
+    if(ctx->traversal == 1)
+        trace_samples_kernel<LinksTrav<false>><<<blocks, threads, 0, ctx->stream>>>(sc, (uint32_t*)ctx->scratch_a.p, (int32_t*)ctx->scratch_b.p, n, (float*)ctx->scratch_c.p);
+    else
+        trace_samples_kernel<WideTrav><<<blocks, threads, 0, ctx->stream>>>(sc, (uint32_t*)ctx->scratch_a.p, (int32_t*)ctx->scratch_b.p, n, (float*)ctx->scratch_c.p);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out_rgb, ctx->scratch_c.p, n * 12, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int ptgpu_tonemap(ptgpu_ctx* ctx, const float* rgb, size_t n, uint8_t* out_bgra)
+{
+    if(!ctx) return 1;
+    if(n == 0) return 0;
+    if(!rgb || !out_bgra) return fail(ctx, "ptgpu_tonemap: null argument");
+    if(use(ctx)) return 1;
+    CK(ctx->scratch_a.reserve(n * 12)); CK(ctx->scratch_b.reserve(n * 4));
+    CK(cudaMemcpyAsync(ctx->scratch_a.p, rgb, n * 12, cudaMemcpyHostToDevice, ctx->stream));
+    tonemap_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>((float*)ctx->scratch_a.p, n, (uchar4*)ctx->scratch_b.p);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out_bgra, ctx->scratch_b.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int ptgpu_trace_closest(ptgpu_ctx* ctx, const float* rays, size_t n, uint32_t subframe, float* out_f, uint32_t* out_u)
+{
+    if(check_ready(ctx)) return 1;
+    if(n == 0) return 0;
+    if(!rays || !out_f || !out_u) return fail(ctx, "ptgpu_trace_closest: null argument");
+    if(subframe >= ctx->n_subframes) return fail(ctx, "ptgpu_trace_closest: subframe %u of %zu", subframe, ctx->n_subframes);
+    if(use(ctx)) return 1;
+    CK(ctx->scratch_a.reserve(n * 32)); CK(ctx->scratch_b.reserve(n * 16)); CK(ctx->scratch_c.reserve(n * 12));
+    CK(cudaMemcpyAsync(ctx->scratch_a.p, rays, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+    Scene sc = make_scene(ctx);
+    const int threads = 128; const int blocks = (int)((n + threads - 1) / threads);
+    if(ctx->traversal == 1)
+        trace_closest_kernel<LinksTrav<false>><<<blocks, threads, 0, ctx->stream>>>(sc, (float*)ctx->scratch_a.p, n, subframe, (float*)ctx->scratch_b.p, (uint32_t*)ctx->scratch_c.p);
+    else
+        trace_closest_kernel<WideTrav><<<blocks, threads, 0, ctx->stream>>>(sc, (float*)ctx->scratch_a.p, n, subframe, (float*)ctx->scratch_b.p, (uint32_t*)ctx->scratch_c.p);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out_f, ctx->scratch_b.p, n * 16, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(out_u, ctx->scratch_c.p, n * 12, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int ptgpu_pcg4d(ptgpu_ctx* ctx, uint32_t* states, size_t n, int32_t steps)
+{
+    if(!ctx) return 1;
+    if(n == 0) return 0;
+    if(!states) return fail(ctx, "ptgpu_pcg4d: null argument");
+    if(use(ctx)) return 1;
+    CK(ctx->scratch_a.reserve(n * 16));
+    CK(cudaMemcpyAsync(ctx->scratch_a.p, states, n * 16, cudaMemcpyHostToDevice, ctx->stream));
+    pcg4d_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>((uint32_t*)ctx->scratch_a.p, n, steps);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(states, ctx->scratch_a.p, n * 16, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int ptgpu_set_option(ptgpu_ctx* ctx, const char* key, int64_t value)
+{
+    if(!ctx || !key) return 1;
+    if(!strcmp(key, "traversal")) { if(value != 0 && value != 1) return fail(ctx, "traversal must be 0 or 1"); ctx->traversal = (int)value; ctx->have_frame = false; return 0; }
+    if(!strcmp(key, "counters")) { ctx->counters_on = value != 0; return 0; }
+    if(!strcmp(key, "kernel")) { if(value != 0 && value != 1) return fail(ctx, "kernel must be 0 or 1"); ctx->kernel = (int)value; return 0; }
+    return fail(ctx, "unknown option '%s'", key);
+}
+
+int ptgpu_read_counters(ptgpu_ctx* ctx, uint64_t out[PTGPU_CNT_COUNT])
+{
+    if(!ctx || !out) return 1;
+    if(use(ctx)) return 1;
+    CK(cudaStreamSynchronize(ctx->stream));
+    Counters h;
+    CK(cudaMemcpy(&h, ctx->counters.p, sizeof(h), cudaMemcpyDeviceToHost));
+    CK(cudaMemset(ctx->counters.p, 0, sizeof(Counters)));
+    for(int i = 0; i < PTGPU_CNT_COUNT; ++i) out[i] = h.v[i];
+    return 0;
+}
+
+int ptgpu_scene_stats(ptgpu_ctx* ctx, uint64_t out[8])
+{
+    if(!ctx || !out) return 1;
+    const WideScene& w = ctx->wide_host;
+    uint64_t ref_bytes = ctx->n_static_nodes * (24 + 64) + ctx->n_indices * 4 + ctx->n_verts * 64 + ctx->n_static * 160;
+    uint64_t wide_bytes = w.nodes.size() * sizeof(WideNode) + w.tris.size() * 16 + w.tlas.size() * sizeof(WideNode) +
+        ctx->n_static * sizeof(WideInstance) + ctx->n_indices * 4 + ctx->n_verts * 48 + ctx->n_static * 160;
+    out[0] = wide_bytes;
+    out[1] = ctx->n_subframes * 160 + ctx->n_dyn * (160 + sizeof(WideInstance)) + ctx->n_subframes * 8;
+    out[2] = w.nodes.size();
+    out[3] = w.tris.size() / 3;
+    out[4] = ctx->n_static;
+    out[5] = w.tlas.size();
+    out[6] = ref_bytes;
+    out[7] = w.blas.size();
+    return 0;
+}
+
+} // extern "C"
