@@ -218,6 +218,15 @@ int ptgpu_read_counters(ptgpu_ctx* ctx, uint64_t out[PTGPU_CNT_COUNT]);
  * wide-BVH nodes, triangles, static instances}. */
 int ptgpu_scene_stats(ptgpu_ctx* ctx, uint64_t out[8]);
 
+/* Host-only, needs no GPU: runs the BVH flattening that ptgpu_upload_static performs on the
+ * reference arrays (bvh.cc:43-229 output) and checks the result structurally (every triangle
+ * reachable exactly once, boxes nested, every static instance in the TLAS once).
+ * out = {BLAS count, wide nodes, triangles, TLAS nodes, stack bound, violations, stack capacity, 0}. */
+int ptgpu_host_flatten_check(
+    const ptgpu_bvh_node* nodes, size_t n_nodes, const ptgpu_bvh_link* links, size_t n_links,
+    const uint32_t* indices, size_t n_indices, const ptgpu_float3* pos, size_t n_verts,
+    const ptgpu_tlas_instance* instances, size_t n_static, uint64_t out[8], char* err, size_t err_len);
+
 #ifdef __cplusplus
 }
 #endif

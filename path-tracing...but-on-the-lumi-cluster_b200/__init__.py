@@ -7,3 +7,5 @@ there is no CPU fallback, and nothing in this package touches `oracle/`.
 from .capi import (Config, LibraryMissing, PtgpuError, lib_path, load_library)  # noqa: F401
 from .renderer import Renderer  # noqa: F401
 from . import scene_io  # noqa: F401
+from . import sharding  # noqa: F401
+from . import capi  # noqa: F401

@@ -472,4 +472,75 @@ bool build_wide_scene(
     return true;
 }
 
+// Structural check of a flattened scene, used by the CPU test-suite: every triangle of every BLAS is
+// reachable exactly once, child boxes enclose what is below them, every static instance is a TLAS
+// leaf exactly once. Returns the number of violations.
+uint64_t verify_wide_scene(const WideScene& ws, size_t n_static, std::string& err)
+{
+    uint64_t bad = 0;
+    auto fail = [&](const std::string& m) { if(bad++ == 0) err = m; };
+    for(size_t b = 0; b < ws.blas.size(); ++b)
+    {
+        const WideBlas& wb = ws.blas[b];
+        std::vector<uint8_t> seen(wb.tri_count, 0);
+        std::vector<uint32_t> prim_seen(wb.tri_count, 0);
+        struct Todo { uint32_t node; Box box; bool has_box; };
+        std::vector<Todo> todo{{0u, Box(), false}};
+        while(!todo.empty())
+        {
+            Todo t = todo.back(); todo.pop_back();
+            if(t.node >= wb.node_count) { fail("child index outside the BLAS"); continue; }
+            const WideNode& n = ws.nodes[wb.node_offset + t.node];
+            const float* lox = &n.lox.x; const float* loy = &n.loy.x; const float* loz = &n.loz.x;
+            const float* hix = &n.hix.x; const float* hiy = &n.hiy.x; const float* hiz = &n.hiz.x;
+            const uint32_t* ch = &n.child.x;
+            for(int i = 0; i < 4; ++i)
+            {
+                if(ch[i] == 0xFFFFFFFFu) continue;
+                Box cb;
+                cb.lo[0] = lox[i]; cb.lo[1] = loy[i]; cb.lo[2] = loz[i];
+                cb.hi[0] = hix[i]; cb.hi[1] = hiy[i]; cb.hi[2] = hiz[i];
+                if(t.has_box)
+                    for(int a = 0; a < 3; ++a)
+                        if(cb.lo[a] < t.box.lo[a] || cb.hi[a] > t.box.hi[a]) fail("child box not inside its parent's slot box");
+                if(!(ch[i] & 0x80000000u)) { todo.push_back({ch[i], cb, true}); continue; }
+                const uint32_t first = ch[i] & 0x07FFFFFFu, count = ((ch[i] >> 27) & 0xFu) + 1u;
+                if(count > (uint32_t)WIDE_LEAF_MAX || first + count > wb.tri_count) { fail("leaf range outside the BLAS"); continue; }
+                for(uint32_t k = 0; k < count; ++k)
+                {
+                    if(seen[first + k]++) fail("triangle slot reachable twice");
+                    const float4* v = &ws.tris[3 * (size_t)(wb.tri_offset + first + k)];
+                    uint32_t prim; memcpy(&prim, &v[0].w, 4);
+                    if(prim >= wb.tri_count) fail("primitive id out of range"); else prim_seen[prim]++;
+                    for(int c = 0; c < 3; ++c)
+                    {
+                        const float p[3] = {v[c].x, v[c].y, v[c].z};
+                        for(int a = 0; a < 3; ++a) if(p[a] < cb.lo[a] || p[a] > cb.hi[a]) fail("triangle vertex outside its leaf box");
+                    }
+                }
+            }
+        }
+        for(uint32_t k = 0; k < wb.tri_count; ++k)
+            if(seen[k] != 1 || prim_seen[k] != 1) { fail("BLAS " + std::to_string(b) + ": triangle missing or duplicated"); break; }
+    }
+    // TLAS
+    std::vector<uint32_t> inst_seen(n_static, 0);
+    std::vector<uint32_t> todo{0u};
+    while(!todo.empty())
+    {
+        uint32_t ni = todo.back(); todo.pop_back();
+        if(ni >= ws.tlas.size()) { fail("TLAS child outside the array"); continue; }
+        const uint32_t* ch = &ws.tlas[ni].child.x;
+        for(int i = 0; i < 4; ++i)
+        {
+            if(ch[i] == 0xFFFFFFFFu) continue;
+            if(!(ch[i] & 0x80000000u)) { todo.push_back(ch[i]); continue; }
+            uint32_t id = ch[i] & 0x7FFFFFFFu;
+            if(id >= n_static) fail("TLAS leaf beyond the static instances"); else inst_seen[id]++;
+        }
+    }
+    for(size_t i = 0; i < n_static; ++i) if(inst_seen[i] != 1) { fail("static instance missing from the TLAS or duplicated"); break; }
+    return bad;
+}
+
 } // namespace pt

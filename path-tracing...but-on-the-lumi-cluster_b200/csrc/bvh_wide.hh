@@ -40,4 +40,7 @@ bool build_wide_scene(
 // Fills the traversal record of one instance (static or per-frame). False if its BLAS is unknown.
 bool make_wide_instance(const WideScene& ws, const ptgpu_tlas_instance& inst, uint32_t ref_index, WideInstance& out);
 
+// Structural self-check of a flattened scene (CPU tests). Returns the number of violations.
+uint64_t verify_wide_scene(const WideScene& ws, size_t n_static, std::string& err);
+
 } // namespace pt

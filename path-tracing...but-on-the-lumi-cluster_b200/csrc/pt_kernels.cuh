@@ -14,6 +14,7 @@ struct RenderJob
     uchar4* out_bgra;      // w*h BGRA (tonemap_pixel), row 0 = top, or null
     uint8_t* out_bmp;      // full BMP file image (bmp.cc:15-52) for a full-frame job, or null
     uint32_t bmp_pitch;
+    int32_t min_active;    // megakernel: leave the traversal loop when fewer lanes than this still traverse
 };
 
 constexpr int TILE_W = 8, TILE_H = 4, SAMPLE_LANES = 8;

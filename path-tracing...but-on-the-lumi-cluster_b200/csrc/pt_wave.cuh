@@ -1,0 +1,499 @@
+// Wavefront renderer: the same per-sample algorithm as pt_mega.cuh (path_trace_pixel,
+// path_tracer.hh:637-741) split into homogeneous kernels over a pool of path slots.
+//
+// Why: in the megakernel ncu measured 6.9 of 32 lanes active per instruction — traversal lengths
+// vary so much that a warp mostly waits for its slowest ray, and shading runs for the few lanes that
+// happen to be done. Here
+//   * wf_trace is a persistent kernel in which a lane whose ray ends immediately takes the next
+//     ray from a global queue (closest-hit and shadow rays alike), so traversal lanes stay busy;
+//   * wf_shade<FAR> processes finished closest-hit queries sorted into two queues: FAR (miss or
+//     t >= 1e3: needs the sky ray-march, path_tracer.hh:513) and NEAR (skips it);
+//   * wf_generate starts the next sample of slots whose path ended (camera rays, :655-671).
+// A slot is (pixel, sample lane l): it traces samples k = l, l+8, ... of the job's sample set one
+// after another and keeps their running sum, exactly like a lane of the megakernel, so both give
+// identical images. All slots of the job live in the pool at once (state ~150 B per slot in HBM).
+#pragma once
+#include "pt_kernels.cuh"
+#include "pt_wide.cuh"
+
+namespace pt {
+
+#define WF_INVALID 0xFFFFFFFFu
+#define WF_SHADOW_BIT 0x80000000u
+
+struct WaveCounters
+{
+    uint32_t n_trace, n_far, n_near, n_new;   // queue extents
+    uint32_t cur_trace;                       // fetch cursor of wf_trace
+    uint32_t active_slots;                    // slots that still have samples to trace
+    uint32_t pad[2];
+};
+
+struct WaveBuffers
+{
+    // per slot
+    uint4* rng;
+    float4* ray_o;        // xyz origin, w tmin
+    float4* ray_d;        // xyz extension-ray direction, w bsdf_pdf of the sample that made it
+    float4* shadow_d;     // xyz NEE direction, w jitter for the attenuation march
+    float4* hit;          // t, u, v, instance (bits)
+    uint32_t* hit_prim;   // primitive | back_face << 31
+    float4* atten;        // xyz path attenuation, w regularization
+    float4* contrib;      // xyz contribution of the current sample, w unused
+    float4* nee;          // xyz pending NEE radiance (before visibility/attenuation), w 1 = pending
+    float4* sum;          // xyz sum over finished samples
+    int2* cursor;         // x = k (index into the sample set), y = bounce
+    uint32_t* visible;    // shadow query result: 1 = unoccluded
+    // queues
+    uint32_t* q_trace;    // slot | WF_SHADOW_BIT
+    uint32_t* q_far;
+    uint32_t* q_near;
+    uint32_t* q_new;
+    WaveCounters* cnt;
+    uint32_t n_slots;
+    int32_t tiles_x;
+};
+
+constexpr int WF_TILE = 8;   // pixels per tile side in the slot order
+
+PT_D bool slot_pixel(const WaveBuffers& wb, const RenderJob& job, uint32_t slot, int& lx, int& ly)
+{
+    const uint32_t pi = slot / SAMPLE_LANES;
+    const uint32_t tile = pi / (WF_TILE * WF_TILE), in = pi % (WF_TILE * WF_TILE);
+    lx = (int)(tile % wb.tiles_x) * WF_TILE + (int)(in % WF_TILE);
+    ly = (int)(tile / wb.tiles_x) * WF_TILE + (int)(in / WF_TILE);
+    return lx < job.w && ly < job.h;
+}
+
+// Warp-aggregated append; must be reached by all 32 lanes of the warp.
+PT_D void wf_append(uint32_t* q, uint32_t* count, bool pred, uint32_t val)
+{
+    const unsigned m = __ballot_sync(0xFFFFFFFFu, pred);
+    if(m == 0u) return;
+    const unsigned lane = threadIdx.x & 31u;
+    uint32_t base = 0;
+    if(lane == (unsigned)(__ffs(m) - 1)) base = atomicAdd(count, (uint32_t)__popc(m));
+    base = __shfl_sync(0xFFFFFFFFu, base, __ffs(m) - 1);
+    if(pred) q[base + __popc(m & ((1u << lane) - 1u))] = val;
+}
+
+// ---- init: every slot starts idle; valid ones are queued for their first sample ---------------
+__global__ void wf_init_kernel(WaveBuffers wb, RenderJob job)
+{
+    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if(slot >= wb.n_slots) return;
+    int lx, ly;
+    const bool valid = slot_pixel(wb, job, slot, lx, ly) && (int)(slot % SAMPLE_LANES) < job.s_count;
+    wb.sum[slot] = make_float4(0, 0, 0, 0);
+    wb.cursor[slot] = make_int2((int)(slot % SAMPLE_LANES), 0);
+    wb.q_new[slot] = valid ? slot : WF_INVALID;
+    if(slot == 0)
+    {
+        wb.cnt->n_new = wb.n_slots; wb.cnt->n_trace = 0; wb.cnt->n_far = 0; wb.cnt->n_near = 0; wb.cnt->cur_trace = 0;
+    }
+}
+
+// ---- generate: camera ray of the slot's next sample (path_tracer.hh:655-671) --------------------
+__global__ void __launch_bounds__(256)
+wf_generate_kernel(Scene sc, RenderJob job, WaveBuffers wb)
+{
+    const uint32_t n = wb.cnt->n_new;
+    const uint32_t rounded = (n + 31u) & ~31u;
+    for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < rounded; i += gridDim.x * blockDim.x)
+    {
+        const uint32_t slot = i < n ? wb.q_new[i] : WF_INVALID;
+        const bool ok = slot != WF_INVALID;
+        if(ok)
+        {
+            int lx, ly;
+            slot_pixel(wb, job, slot, lx, ly);
+            const int k = wb.cursor[slot].x;
+            const int sample = job.s_begin + k * job.s_stride;
+            const uint32_t px = (uint32_t)(job.x0 + lx), py = (uint32_t)(job.y0 + ly);
+            const uint32_t subframe = sample < 0 ? 0u : (uint32_t)sample / (uint32_t)sc.samples_per_subframe;
+            rng4 seed = {px, py, (uint32_t)sample, sc.student_id};
+            pcg4d(seed);
+            float4 u = rand4(seed);
+            v2 film = sample_gaussian_disk(u.x, u.y, 0.4f);
+            v3 d, o;
+            camera_ray(sc, sc.subframes + subframe, u.z, u.w, (float)px + (film.x + 0.5f), (float)py + (film.y + 0.5f), d, o);
+            wb.rng[slot] = make_uint4(seed.x, seed.y, seed.z, seed.w);
+            wb.ray_o[slot] = make_float4(o.x, o.y, o.z, 0.0f);
+            wb.ray_d[slot] = make_float4(d.x, d.y, d.z, -1.0f); // bsdf_pdf -1: MIS weight 1, |pdf| 1, no regularisation
+            wb.atten[slot] = make_float4(1, 1, 1, 1);
+            wb.contrib[slot] = make_float4(0, 0, 0, 0);
+            wb.nee[slot] = make_float4(0, 0, 0, 0);
+            wb.cursor[slot] = make_int2(k, 0);
+        }
+        wf_append(wb.q_trace, &wb.cnt->n_trace, ok, slot);
+    }
+}
+
+// ---- trace: persistent traversal kernel -----------------------------------------------------------
+constexpr int WF_TRACE_THREADS = 128;
+constexpr int WF_FETCH_CHUNK = 64;
+
+__global__ void __launch_bounds__(WF_TRACE_THREADS, 6)
+wf_trace_kernel(Scene sc, RenderJob job, WaveBuffers wb)
+{
+    const unsigned lane = threadIdx.x & 31u;
+    const uint32_t n_entries = wb.cnt->n_trace;
+
+    // warp-uniform reserve of queue entries [res_base, res_base + res_n)
+    uint32_t res_base = 0, res_n = 0;
+    bool exhausted = false;
+    // warp-uniform output chunks (32 entries each) for the two result queues
+    uint32_t far_base = 0, far_fill = 32, near_base = 0, near_fill = 32;
+
+    bool active = false;
+    int done_class = 0;               // 0 none, 1 near, 2 far (closest-hit query finished, not yet queued)
+    uint32_t slot = 0;
+    bool shadow_ray = false;
+    uint32_t subframe = 0;
+
+    uint32_t stack[WIDE_STACK];
+    int sp = 0;
+    uint32_t cur = PT_EMPTY;
+    v3 ro = mk3(0, 0, 0), rd = mk3(0, 0, 1);
+    v3 o = ro, d = rd, inv = mk3(0, 0, 0), S = mk3(0, 0, 1);
+    int axis = 2;
+    bool in_blas = false;
+    const WideNode* nodes = sc.wtlas;
+    const float4* tris = sc.wtris;
+    uint32_t cur_inst = 0;
+    float tmin = 0.0f, tmax = 0.0f;
+    Hit hit; hit.t = -1.0f; hit.u = hit.v = 0.0f; hit.inst = 0; hit.prim = 0; hit.back_face = false;
+
+    for(;;)
+    {
+        const unsigned act = __ballot_sync(0xFFFFFFFFu, active);
+        // refill when at least job.min_active lanes are idle (or nothing is running)
+        if(__popc(act) <= 32 - job.min_active || act == 0u)
+        {
+            // -- queue finished closest-hit queries by class, in 32-entry chunks per warp --------------
+            #pragma unroll
+            for(int cls = 1; cls <= 2; ++cls)
+            {
+                const unsigned m = __ballot_sync(0xFFFFFFFFu, done_class == cls);
+                if(m == 0u) continue;
+                uint32_t& base = cls == 1 ? near_base : far_base;
+                uint32_t& fill = cls == 1 ? near_fill : far_fill;
+                uint32_t* q = cls == 1 ? wb.q_near : wb.q_far;
+                uint32_t* qn = cls == 1 ? &wb.cnt->n_near : &wb.cnt->n_far;
+                const uint32_t cnt = (uint32_t)__popc(m);
+                const uint32_t rank = (uint32_t)__popc(m & ((1u << lane) - 1u));
+                const uint32_t room = 32u - fill;
+                uint32_t new_base = 0;
+                if(cnt > room)
+                {
+                    if(lane == 0) new_base = atomicAdd(qn, 32u);
+                    new_base = __shfl_sync(0xFFFFFFFFu, new_base, 0);
+                }
+                if(done_class == cls)
+                {
+                    if(rank < room) q[base + fill + rank] = slot;
+                    else q[new_base + (rank - room)] = slot;
+                    done_class = 0;
+                }
+                if(cnt > room)
+                {
+                    base = new_base; fill = cnt - room;
+                }
+                else fill += cnt;
+            }
+            // -- refill idle lanes from the ray queue ------------------------------------------------
+            const unsigned idle = ~act;
+            uint32_t want = (uint32_t)__popc(idle);
+            const uint32_t my_rank = (uint32_t)__popc(idle & ((1u << lane) - 1u));
+            uint32_t entry_index = WF_INVALID;
+            uint32_t served = 0;
+            while(want > served && !(exhausted && res_n == 0u))
+            {
+                if(res_n == 0u)
+                {
+                    uint32_t b = 0;
+                    if(lane == 0) b = atomicAdd(&wb.cnt->cur_trace, (uint32_t)WF_FETCH_CHUNK);
+                    b = __shfl_sync(0xFFFFFFFFu, b, 0);
+                    if(b >= n_entries) { exhausted = true; break; }
+                    res_base = b;
+                    res_n = min((uint32_t)WF_FETCH_CHUNK, n_entries - b);
+                }
+                const uint32_t take = min(res_n, want - served);
+                if(!active && my_rank >= served && my_rank < served + take) entry_index = res_base + (my_rank - served);
+                res_base += take; res_n -= take; served += take;
+            }
+            if(entry_index != WF_INVALID)
+            {
+                const uint32_t e = __ldg(wb.q_trace + entry_index);
+                if(e != WF_INVALID)
+                {
+                    slot = e & ~WF_SHADOW_BIT;
+                    shadow_ray = (e & WF_SHADOW_BIT) != 0u;
+                    const float4 fo = wb.ray_o[slot];
+                    const float4 fd = shadow_ray ? wb.shadow_d[slot] : wb.ray_d[slot];
+                    const int sample = job.s_begin + wb.cursor[slot].x * job.s_stride;
+                    subframe = sample < 0 ? 0u : (uint32_t)sample / (uint32_t)sc.samples_per_subframe;
+                    ro = mk3(fo.x, fo.y, fo.z); rd = mk3(fd.x, fd.y, fd.z);
+                    tmin = fo.w; tmax = PT_MAX_RAY_DIST;
+                    // query start: dynamic instances of the subframe, then the static TLAS root
+                    hit.t = -1.0f; hit.u = 0.0f; hit.v = 0.0f; hit.inst = 0xFFFFFFFFu; hit.prim = 0; hit.back_face = false;
+                    sp = 0;
+                    o = ro; d = rd; inv = safe_inv_dir(rd);
+                    in_blas = false; nodes = sc.wtlas;
+                    const uint2 r = __ldg(sc.dyn_range + subframe);
+                    const uint32_t p = r.x, a = r.y & 0xFFFFFu, len = r.y >> 20;
+                    for(uint32_t i = 0; i < p + len; ++i)
+                    {
+                        const uint32_t id = sc.n_static + (i < p ? i : a + (i - p));
+                        const WideInstance* wi = sc.winst + id;
+                        if(box_hit(__ldg(&wi->lo), __ldg(&wi->hi), o, inv, tmin, tmax))
+                            stack[sp++] = 0x80000000u | id;
+                    }
+                    cur = 0;
+                    active = true;
+                }
+            }
+            if(__ballot_sync(0xFFFFFFFFu, active) == 0u)
+            {
+                if(exhausted && res_n == 0u) break;
+                continue;
+            }
+        }
+        // -- advance: pop / complete (cheap, every lane) ---------------------------------------------
+        if(active && cur == PT_EMPTY)
+        {
+            if(sp == 0)
+            {   // query complete: write the result
+                active = false;
+                if(shadow_ray) wb.visible[slot] = hit.t < 0.0f ? 1u : 0u;
+                else
+                {
+                    wb.hit[slot] = make_float4(hit.t, hit.u, hit.v, __uint_as_float(hit.inst));
+                    wb.hit_prim[slot] = hit.prim | (hit.back_face ? 0x80000000u : 0u);
+                    done_class = (hit.t > 0.0f && hit.t < 1e3f) ? 1 : 2;
+                }
+            }
+            else cur = stack[--sp];
+        }
+
+        // -- phase vote: run ONE code block per iteration, the one most lanes are waiting for. ncu on
+        //    the unvoted loop: triangle tests ran with 2.4 of 32 lanes and were 45% of all issued
+        //    instructions; lanes now wait at a leaf until the leaf block is elected.
+        const bool w_inner = active && !(cur & 0x80000000u);
+        const bool w_tri = active && (cur & 0x80000000u) && in_blas && cur != PT_EXIT_MARK;
+        const bool w_xform = active && (cur & 0x80000000u) && (!in_blas || cur == PT_EXIT_MARK);
+        const int n_inner = __popc(__ballot_sync(0xFFFFFFFFu, w_inner));
+        const int n_tri = __popc(__ballot_sync(0xFFFFFFFFu, w_tri));
+        const int n_xform = __popc(__ballot_sync(0xFFFFFFFFu, w_xform));
+        if(n_inner >= n_tri && n_inner >= n_xform)
+        {
+            if(w_inner)
+            {
+                uint32_t key[4]; uint4 child;
+                test4(nodes + cur, o, inv, tmin, tmax, key, child);
+                cswap(key[0], key[1]); cswap(key[2], key[3]); cswap(key[0], key[2]); cswap(key[1], key[3]); cswap(key[1], key[2]);
+                if(key[3] != PT_EMPTY) stack[sp++] = pick_child(child, key[3] & 3u);
+                if(key[2] != PT_EMPTY) stack[sp++] = pick_child(child, key[2] & 3u);
+                if(key[1] != PT_EMPTY) stack[sp++] = pick_child(child, key[1] & 3u);
+                cur = key[0] != PT_EMPTY ? pick_child(child, key[0] & 3u) : PT_EMPTY;
+            }
+        }
+        else if(n_tri >= n_xform)
+        {
+            if(w_tri)
+            {   // one triangle of the leaf per election (ray_query_test_triangle, ray_query.hh:225-246)
+                const uint32_t first = cur & 0x07FFFFFFu, more = (cur >> 27) & 0xFu;
+                const float4* tp = tris + 3 * (size_t)first;
+                const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
+                cur = more ? (0x80000000u | ((more - 1u) << 27) | (first + 1u)) : PT_EMPTY;
+                float u, v, t; bool bf;
+                bool ok = tri_intersect(o, axis, S, mk3(a), mk3(b), mk3(c), u, v, t, bf);
+                if(ok && t < tmax && t > tmin)
+                {
+                    hit.t = t; hit.u = u; hit.v = v; hit.inst = cur_inst; hit.prim = __float_as_uint(a.w); hit.back_face = bf;
+                    tmax = t;
+                    if(shadow_ray) { sp = 0; cur = PT_EMPTY; } // any hit ends a shadow query
+                }
+            }
+        }
+        else if(w_xform)
+        {
+            if(cur == PT_EXIT_MARK)
+            {   // BLAS finished: back to world space
+                in_blas = false; nodes = sc.wtlas; o = ro; d = rd; inv = safe_inv_dir(rd);
+                cur = PT_EMPTY;
+            }
+            else
+            {   // TLAS leaf: enter the instance (ray_query_enter_blas, ray_query.hh:153-182)
+                cur_inst = cur & 0x7FFFFFFFu;
+                const WideInstance* wi = sc.winst + cur_inst;
+                const float4 r0 = __ldg(&wi->inv0), r1 = __ldg(&wi->inv1), r2 = __ldg(&wi->inv2);
+                const uint32_t b = __ldg(&wi->blas);
+                o = mk3(r0.x * ro.x + r0.y * ro.y + r0.z * ro.z + r0.w,
+                        r1.x * ro.x + r1.y * ro.y + r1.z * ro.z + r1.w,
+                        r2.x * ro.x + r2.y * ro.y + r2.z * ro.z + r2.w);
+                d = mk3(r0.x * rd.x + r0.y * rd.y + r0.z * rd.z,
+                        r1.x * rd.x + r1.y * rd.y + r1.z * rd.z,
+                        r2.x * rd.x + r2.y * rd.y + r2.z * rd.z);
+                inv = safe_inv_dir(d);
+                tri_preprocess(d, axis, S);
+                const uint2 bo = __ldg(reinterpret_cast<const uint2*>(sc.wblas + b));
+                nodes = sc.wnodes + bo.x;
+                tris = sc.wtris + 3 * (size_t)bo.y;
+                in_blas = true;
+                stack[sp++] = PT_EXIT_MARK;
+                cur = 0;
+            }
+        }
+    }
+    // pad the partly filled output chunks so that consumers can skip them (fill == 32 with no
+    // reservation is the initial state, so only chunks with fill < 32 exist and need padding)
+    if(near_fill < 32u && near_fill + lane < 32u) wb.q_near[near_base + near_fill + lane] = WF_INVALID;
+    if(far_fill < 32u && far_fill + lane < 32u) wb.q_far[far_base + far_fill + lane] = WF_INVALID;
+}
+
+// ---- shade: a closest-hit query finished (trace_ray tail + bounce loop body) -----------------------
+template<bool FAR>
+__global__ void __launch_bounds__(128)
+wf_shade_kernel(Scene sc, RenderJob job, WaveBuffers wb)
+{
+    const uint32_t n = FAR ? wb.cnt->n_far : wb.cnt->n_near;
+    const uint32_t* q = FAR ? wb.q_far : wb.q_near;
+    const uint32_t rounded = (n + 31u) & ~31u;
+    for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < rounded; i += gridDim.x * blockDim.x)
+    {
+        const uint32_t slot = i < n ? q[i] : WF_INVALID;
+        bool push_ext = false, push_shadow = false, push_new = false;
+        if(slot != WF_INVALID)
+        {
+            int2 cursor = wb.cursor[slot];
+            const int sample = job.s_begin + cursor.x * job.s_stride;
+            const uint32_t subframe = sample < 0 ? 0u : (uint32_t)sample / (uint32_t)sc.samples_per_subframe;
+            const RefSubframe* rsf = sc.subframes + subframe;
+            Light light;
+            light.dir = mk3(__ldg(&rsf->light_dir));
+            light.color = mk3(__ldg(&rsf->light_color));
+            light.cos_solid_angle = __ldg(&rsf->cos_solid_angle);
+
+            const float4 fo = wb.ray_o[slot], fd = wb.ray_d[slot];
+            v3 ray_o = mk3(fo.x, fo.y, fo.z), ray_d = mk3(fd.x, fd.y, fd.z);
+            float bsdf_pdf = fd.w;
+            float4 fa = wb.atten[slot], fc = wb.contrib[slot];
+            v3 attenuation = mk3(fa.x, fa.y, fa.z), contribution = mk3(fc.x, fc.y, fc.z);
+            float regularization = fa.w;
+            const uint4 fs = wb.rng[slot];
+            rng4 seed = {fs.x, fs.y, fs.z, fs.w};
+            int bounce = cursor.y;
+
+            // NEE of the previous bounce (nee_branch tail, path_tracer.hh:611-619)
+            const float4 fn = wb.nee[slot];
+            if(fn.w != 0.0f && wb.visible[slot] != 0u)
+            {
+                const float4 sd = wb.shadow_d[slot];
+                contribution += mk3(fn.x, fn.y, fn.z) * sky_attenuation(sd.w, ray_o, mk3(sd.x, sd.y, sd.z));
+            }
+
+            const float4 fh = wb.hit[slot];
+            const uint32_t hp = wb.hit_prim[slot];
+            Hit hit; hit.t = fh.x; hit.u = fh.y; hit.v = fh.z; hit.inst = __float_as_uint(fh.w);
+            hit.prim = hp & 0x7FFFFFFFu; hit.back_face = (hp & 0x80000000u) != 0u;
+            HitInfo info;
+            shade_hit(sc, light, hit, ray_o, ray_d, info);
+
+            const float mis_pdf = bsdf_pdf < 0.0f ? -bsdf_pdf :
+                (info.nee_pdf * info.nee_pdf + bsdf_pdf * bsdf_pdf) / bsdf_pdf;
+            v3 atmo_att = mk3(1, 1, 1), scat = mk3(0, 0, 0);
+            if(FAR) sky_scattering(seed, light, ray_o, ray_d, info.thit, atmo_att, scat);
+            contribution += attenuation * (scat + atmo_att * info.s.albedo * info.emission) * (1.0f / mis_pdf);
+            attenuation *= atmo_att * (1.0f / fabsf(bsdf_pdf));
+            if(bsdf_pdf > 0.0f)
+                regularization *= fmaxf(1.0f - PT_REG_GAMMA / sqrtf(sqrtf(bsdf_pdf)), 0.0f);
+            if(bounce > 0) info.s.roughness = 1.0f - (1.0f - info.s.roughness) * regularization;
+
+            if(bounce >= sc.max_bounces || !(info.thit > 0.0f))
+            {   // path complete
+                float4 s = wb.sum[slot];
+                s.x += contribution.x; s.y += contribution.y; s.z += contribution.z;
+                wb.sum[slot] = s;
+                cursor.x += SAMPLE_LANES; cursor.y = 0;
+                wb.cursor[slot] = cursor;
+                push_new = cursor.x < job.s_count;
+            }
+            else
+            {
+                bounce++;
+                v3 view = mul_v3m3(-ray_d, info.tbn);
+                if(view.z < 1e-7f) view.z = fmaxf(view.z, 1e-7f);
+                view = normalize(view);
+
+                float4 un = rand4(seed);
+                v3 light_dir = sample_cone(light.dir, light.cos_solid_angle, un.x, un.y);
+                const float nee_pdf = 1.0f / (PT_TWO_PI * (1.0f - light.cos_solid_angle));
+                float eval_pdf = 0.0f;
+                v3 color = bsdf_eval(mul_v3m3(light_dir, info.tbn), view, info.s, eval_pdf) * nee_pdf * light.color;
+                const bool lit = !(color.x == 0.0f && color.y == 0.0f && color.z == 0.0f);
+                float nee_mis = 1.0f;
+                if(light.cos_solid_angle < 1.0f) nee_mis = (nee_pdf * nee_pdf + eval_pdf * eval_pdf) / nee_pdf;
+                v3 nee_pending = attenuation * (color * (1.0f / nee_mis));
+
+                float4 ub = rand4(seed);
+                v3 tdir, bsdf_att;
+                bsdf_sample(ub.x, ub.y, ub.z, view, info.s, tdir, bsdf_att, bsdf_pdf);
+                v3 bounce_d = normalize(mul_m3v3(info.tbn, tdir));
+                attenuation *= bsdf_att;
+
+                wb.ray_o[slot] = make_float4(info.pos.x, info.pos.y, info.pos.z, PT_MIN_RAY_DIST);
+                wb.ray_d[slot] = make_float4(bounce_d.x, bounce_d.y, bounce_d.z, bsdf_pdf);
+                wb.shadow_d[slot] = make_float4(light_dir.x, light_dir.y, light_dir.z, un.w);
+                wb.nee[slot] = make_float4(nee_pending.x, nee_pending.y, nee_pending.z, lit ? 1.0f : 0.0f);
+                wb.atten[slot] = make_float4(attenuation.x, attenuation.y, attenuation.z, regularization);
+                wb.contrib[slot] = make_float4(contribution.x, contribution.y, contribution.z, 0.0f);
+                wb.rng[slot] = make_uint4(seed.x, seed.y, seed.z, seed.w);
+                cursor.y = bounce;
+                wb.cursor[slot] = cursor;
+                push_ext = true;
+                push_shadow = lit;
+            }
+        }
+        wf_append(wb.q_trace, &wb.cnt->n_trace, push_shadow, slot | WF_SHADOW_BIT);
+        wf_append(wb.q_trace, &wb.cnt->n_trace, push_ext, slot);
+        wf_append(wb.q_new, &wb.cnt->n_new, push_new, slot);
+    }
+}
+
+// ---- bookkeeping between phases ----------------------------------------------------------------------
+// phase 0: before generate+shade of the next round consume q_new / results: nothing to do
+// phase 1 (after trace): q_trace consumed -> reset it and the fetch cursor; q_new is refilled by shade
+// phase 2 (after shade): result queues consumed -> reset; report whether any ray is left
+__global__ void wf_phase_kernel(WaveBuffers wb, int phase, uint32_t* host_visible_remaining)
+{
+    if(threadIdx.x != 0 || blockIdx.x != 0) return;
+    WaveCounters* c = wb.cnt;
+    if(phase == 1) { c->n_trace = 0; c->cur_trace = 0; c->n_new = 0; }
+    else if(phase == 2) { c->n_far = 0; c->n_near = 0; if(host_visible_remaining) *host_visible_remaining = c->n_trace + c->n_new; }
+}
+
+// ---- finalize: fixed-order sum of the 8 slots of each pixel, mean, tonemap, pack ----------------------
+__global__ void wf_finalize_kernel(RenderJob job, WaveBuffers wb)
+{
+    const uint32_t pi = blockIdx.x * blockDim.x + threadIdx.x;
+    if(pi * SAMPLE_LANES >= wb.n_slots) return;
+    int lx, ly;
+    if(!slot_pixel(wb, job, pi * SAMPLE_LANES, lx, ly)) return;
+    v3 s[SAMPLE_LANES];
+    #pragma unroll
+    for(int l = 0; l < SAMPLE_LANES; ++l) { float4 f = wb.sum[pi * SAMPLE_LANES + l]; s[l] = mk3(f.x, f.y, f.z); }
+    // same tree as reduce_lanes (xor 1, 2, 4)
+    #pragma unroll
+    for(int m = 1; m < SAMPLE_LANES; m <<= 1)
+    {
+        v3 t[SAMPLE_LANES];
+        #pragma unroll
+        for(int l = 0; l < SAMPLE_LANES; ++l) t[l] = s[l] + s[l ^ m];
+        #pragma unroll
+        for(int l = 0; l < SAMPLE_LANES; ++l) s[l] = t[l];
+    }
+    store_pixel(job, lx, ly, s[0]);
+}
+
+} // namespace pt

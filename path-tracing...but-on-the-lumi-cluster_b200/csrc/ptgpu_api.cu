@@ -3,6 +3,7 @@
 #include "pt_kernels.cuh"
 #include "pt_wide.cuh"
 #include "pt_mega.cuh"
+#include "pt_wave.cuh"
 #include "bvh_wide.hh"
 
 #include <cstdarg>
@@ -56,7 +57,8 @@ struct ptgpu_ctx
     // options
     int traversal = 0; // 0 wide, 1 links
     int counters_on = 0;
-    int kernel = 0;    // 0 megakernel, 1 simple tiles
+    int kernel = 2;    // 0 megakernel, 1 simple tiles, 2 wavefront
+    int min_active = -1; // -1: per-kernel default
 
     // static scene, reference layout
     DevBuf<float2> ref_nodes;     // 3 per node; static region then per-frame TLAS region
@@ -91,6 +93,11 @@ struct ptgpu_ctx
     DevBuf<float> out_rgb;
     DevBuf<Counters> counters;
     DevBuf<MegaState> mega_state;
+    // wavefront pool
+    DevBuf<uint8_t> wave_mem;
+    DevBuf<uint32_t> wave_flag;
+    uint32_t* wave_flag_host = nullptr;
+    int last_wave_rounds = 0;
     uint32_t bmp_pitch = 0;
     bool bmp_header_done = false;
     bool render_pending = false;
@@ -162,6 +169,68 @@ int check_ready(ptgpu_ctx* ctx)
     return 0;
 }
 
+// Carves the wavefront pool out of one allocation and runs rounds of generate / trace / shade until
+// no slot has a ray or a sample left. Returns kernels launched, or -1.
+int launch_wave(ptgpu_ctx* ctx, const Scene& sc, RenderJob job)
+{
+    const int tiles_x = (job.w + WF_TILE - 1) / WF_TILE, tiles_y = (job.h + WF_TILE - 1) / WF_TILE;
+    const uint32_t n_slots = (uint32_t)tiles_x * tiles_y * WF_TILE * WF_TILE * SAMPLE_LANES;
+    const size_t q_pad = 32u * 1024u * 16u;
+    size_t off = 0;
+    auto carve = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~size_t(255); return o; };
+    const size_t o_rng = carve(16ull * n_slots), o_ro = carve(16ull * n_slots), o_rd = carve(16ull * n_slots),
+        o_sd = carve(16ull * n_slots), o_hit = carve(16ull * n_slots), o_prim = carve(4ull * n_slots),
+        o_att = carve(16ull * n_slots), o_con = carve(16ull * n_slots), o_nee = carve(16ull * n_slots),
+        o_sum = carve(16ull * n_slots), o_cur = carve(8ull * n_slots), o_vis = carve(4ull * n_slots),
+        o_qt = carve(4ull * (2ull * n_slots + q_pad)), o_qf = carve(4ull * (n_slots + q_pad)),
+        o_qn = carve(4ull * (n_slots + q_pad)), o_qw = carve(4ull * (n_slots + q_pad)), o_cnt = carve(sizeof(WaveCounters));
+    if(ctx->wave_mem.reserve(off) != cudaSuccess) return -1;
+    if(!ctx->wave_flag_host)
+    {
+        if(cudaMallocHost(&ctx->wave_flag_host, 64) != cudaSuccess) return -1;
+        if(ctx->wave_flag.reserve(16) != cudaSuccess) return -1;
+    }
+    uint8_t* m = ctx->wave_mem.p;
+    WaveBuffers wb{};
+    wb.rng = (uint4*)(m + o_rng); wb.ray_o = (float4*)(m + o_ro); wb.ray_d = (float4*)(m + o_rd);
+    wb.shadow_d = (float4*)(m + o_sd); wb.hit = (float4*)(m + o_hit); wb.hit_prim = (uint32_t*)(m + o_prim);
+    wb.atten = (float4*)(m + o_att); wb.contrib = (float4*)(m + o_con); wb.nee = (float4*)(m + o_nee);
+    wb.sum = (float4*)(m + o_sum); wb.cursor = (int2*)(m + o_cur); wb.visible = (uint32_t*)(m + o_vis);
+    wb.q_trace = (uint32_t*)(m + o_qt); wb.q_far = (uint32_t*)(m + o_qf); wb.q_near = (uint32_t*)(m + o_qn);
+    wb.q_new = (uint32_t*)(m + o_qw); wb.cnt = (WaveCounters*)(m + o_cnt);
+    wb.n_slots = n_slots; wb.tiles_x = tiles_x;
+    if(job.min_active < 1) job.min_active = 1;
+
+    cudaStream_t st = ctx->stream;
+    int launches = 0;
+    wf_init_kernel<<<(n_slots + 255) / 256, 256, 0, st>>>(wb, job); launches++;
+    const int sms = ctx->sm_count;
+    // worst case: every sample of a slot takes all bounces
+    const int samples_per_slot = (job.s_count + SAMPLE_LANES - 1) / SAMPLE_LANES;
+    const int max_rounds = samples_per_slot * (sc.max_bounces + 1) + 2;
+    const int check_every = 8;
+    int rounds = 0;
+    for(;;)
+    {
+        for(int b = 0; b < check_every && rounds < max_rounds; ++b, ++rounds)
+        {
+            wf_generate_kernel<<<sms * 4, 256, 0, st>>>(sc, job, wb);
+            wf_trace_kernel<<<sms * 6, WF_TRACE_THREADS, 0, st>>>(sc, job, wb);
+            wf_phase_kernel<<<1, 32, 0, st>>>(wb, 1, nullptr);
+            wf_shade_kernel<true><<<sms * 8, 128, 0, st>>>(sc, job, wb);
+            wf_shade_kernel<false><<<sms * 8, 128, 0, st>>>(sc, job, wb);
+            wf_phase_kernel<<<1, 32, 0, st>>>(wb, 2, ctx->wave_flag.p);
+            launches += 6;
+        }
+        if(cudaMemcpyAsync(ctx->wave_flag_host, ctx->wave_flag.p, 4, cudaMemcpyDeviceToHost, st) != cudaSuccess) return -1;
+        if(cudaStreamSynchronize(st) != cudaSuccess) return -1;
+        if(*ctx->wave_flag_host == 0u || rounds >= max_rounds) break;
+    }
+    ctx->last_wave_rounds = rounds;
+    wf_finalize_kernel<<<(n_slots / SAMPLE_LANES + 255) / 256, 256, 0, st>>>(job, wb); launches++;
+    return launches;
+}
+
 // Launch one render job on the context's stream. Returns kernels launched, or -1.
 int launch_job(ptgpu_ctx* ctx, const RenderJob& job)
 {
@@ -182,9 +251,13 @@ int launch_job(ptgpu_ctx* ctx, const RenderJob& job)
         render_tiles_kernel<WideTrav, false><<<tiles, TILE_THREADS, 0, ctx->stream>>>(sc, job, nullptr);
         launches = 1;
     }
-    else
+    else if(ctx->kernel == 0)
     {
         launches = launch_mega(sc, job, ctx->mega_state.p, ctx->sm_count, ctx->stream);
+    }
+    else
+    {
+        launches = launch_wave(ctx, sc, job);
     }
     if(cudaGetLastError() != cudaSuccess) return -1;
     return launches;
@@ -303,7 +376,8 @@ void ptgpu_destroy(ptgpu_ctx* ctx)
     ctx->instances.release(); ctx->wnodes.release(); ctx->wtris.release(); ctx->wblas.release();
     ctx->winst.release(); ctx->wtlas.release(); ctx->subframes.release(); ctx->dyn_range.release();
     ctx->out_bgra.release(); ctx->out_bmp.release(); ctx->out_rgb.release(); ctx->counters.release();
-    ctx->mega_state.release();
+    ctx->mega_state.release(); ctx->wave_mem.release(); ctx->wave_flag.release();
+    if(ctx->wave_flag_host) cudaFreeHost(ctx->wave_flag_host);
     ctx->scratch_a.release(); ctx->scratch_b.release(); ctx->scratch_c.release();
     if(ctx->pinned) cudaFreeHost(ctx->pinned);
     cudaEventDestroy(ctx->ev_begin); cudaEventDestroy(ctx->ev_end);
@@ -485,6 +559,7 @@ static int render_full(ptgpu_ctx* ctx, bool bgra, bool bmp)
     job.out_bgra = bgra ? ctx->out_bgra.p : nullptr;
     job.out_bmp = bmp ? ctx->out_bmp.p : nullptr;
     job.bmp_pitch = ctx->bmp_pitch;
+    job.min_active = ctx->min_active < 0 ? (ctx->kernel == 2 ? 1 : 0) : ctx->min_active;
     int launches = 0;
     CK(cudaEventRecord(ctx->ev_begin, ctx->stream));
     if(bmp && !ctx->bmp_header_done)
@@ -599,6 +674,7 @@ int ptgpu_render_rect(
     job.x0 = x0; job.y0 = y0; job.w = w; job.h = h;
     job.s_begin = s_begin; job.s_count = s_count; job.s_stride = s_stride;
     job.out_rgb = ctx->out_rgb.p; job.out_bgra = d_bgra; job.out_bmp = nullptr; job.bmp_pitch = 0;
+    job.min_active = ctx->min_active < 0 ? (ctx->kernel == 2 ? 1 : 0) : ctx->min_active;
     CK(cudaEventRecord(ctx->ev_begin, ctx->stream));
     int l = launch_job(ctx, job);
     if(l < 0) { tmp_bgra.release(); return fail(ctx, "kernel launch failed: %s", cudaGetErrorString(cudaGetLastError())); }
@@ -693,7 +769,8 @@ int ptgpu_set_option(ptgpu_ctx* ctx, const char* key, int64_t value)
     if(!ctx || !key) return 1;
     if(!strcmp(key, "traversal")) { if(value != 0 && value != 1) return fail(ctx, "traversal must be 0 or 1"); ctx->traversal = (int)value; ctx->have_frame = false; return 0; }
     if(!strcmp(key, "counters")) { ctx->counters_on = value != 0; return 0; }
-    if(!strcmp(key, "kernel")) { if(value != 0 && value != 1) return fail(ctx, "kernel must be 0 or 1"); ctx->kernel = (int)value; return 0; }
+    if(!strcmp(key, "kernel")) { if(value < 0 || value > 2) return fail(ctx, "kernel must be 0, 1 or 2"); ctx->kernel = (int)value; return 0; }
+    if(!strcmp(key, "min_active")) { if(value < -1 || value > 32) return fail(ctx, "min_active must be -1..32"); ctx->min_active = (int)value; return 0; }
     return fail(ctx, "unknown option '%s'", key);
 }
 
@@ -725,6 +802,26 @@ int ptgpu_scene_stats(ptgpu_ctx* ctx, uint64_t out[8])
     out[6] = ref_bytes;
     out[7] = w.blas.size();
     return 0;
+}
+
+int ptgpu_host_flatten_check(
+    const ptgpu_bvh_node* nodes, size_t n_nodes, const ptgpu_bvh_link* links, size_t n_links,
+    const uint32_t* indices, size_t n_indices, const ptgpu_float3* pos, size_t n_verts,
+    const ptgpu_tlas_instance* instances, size_t n_static, uint64_t out[8], char* err, size_t err_len)
+{
+    std::string e;
+    WideScene ws;
+    if(err && err_len) err[0] = 0;
+    if(!nodes || !links || !indices || !pos || !instances || !out || n_links != 8 * n_nodes) e = "bad arguments";
+    else if(build_wide_scene(nodes, n_nodes, links, indices, n_indices, pos, n_verts, instances, n_static, ws, e))
+    {
+        uint64_t bad = verify_wide_scene(ws, n_static, e);
+        out[0] = ws.blas.size(); out[1] = ws.nodes.size(); out[2] = ws.tris.size() / 3; out[3] = ws.tlas.size();
+        out[4] = ws.max_stack; out[5] = bad; out[6] = WIDE_STACK; out[7] = 0;
+        if(bad == 0) return 0;
+    }
+    if(err && err_len) { strncpy(err, e.c_str(), err_len - 1); err[err_len - 1] = 0; }
+    return 1;
 }
 
 } // extern "C"

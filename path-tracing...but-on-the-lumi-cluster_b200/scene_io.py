@@ -27,7 +27,7 @@ def frame_path(frame, tag="testing"):
 
 
 def save_static(path, view):
-    """view: dict from oracle.refbind.Oracle.view() (before any frame TLAS is appended, or with
+    """view: dict of the seam arrays plus n_static_nodes / n_static_instances (any frame; with
     n_static_nodes marking the end of the BLAS region)."""
     n = view["n_static_nodes"]
     ns = view["n_static_instances"]
