@@ -47,7 +47,8 @@ class Config(C.Structure):
 
 
 def lib_path():
-    return os.path.join(HERE, "libptgpu.so")
+    # PTGPU_LIB: developer override to load an experimental build of the same library
+    return os.environ.get("PTGPU_LIB") or os.path.join(HERE, "libptgpu.so")
 
 
 _lib = None

@@ -319,6 +319,261 @@ void build_sah(std::vector<Prim>& prims, size_t begin, size_t end, std::vector<T
     build_sah(prims, best_split, end, tree, first + 1);
 }
 
+// ---- compressed 8-wide BVH (after Ylitie, Karras, Laine 2017) --------------------------------------
+//
+// Node = 80 bytes = 5 x 16-byte loads:
+//   n0  p.x p.y p.z | e.x e.y e.z imask      origin of the quantisation grid, per-axis exponent, inner mask
+//   n1  child_base | tri_base | meta[0..3] | meta[4..7]
+//   n2  qlo.x[0..7] | qlo.y[0..7]             child boxes, 8 bits per bound: lo = p + q * 2^e
+//   n3  qlo.z[0..7] | qhi.x[0..7]
+//   n4  qhi.y[0..7] | qhi.z[0..7]
+// meta[slot]: inner child 0b001_11sss (24 + slot); leaf 0b{unary count}_{offset from tri_base}; 0 = empty.
+// Children sit in the slot whose octant direction best matches their offset from the node centre, so
+// a ray visits slots in the order (slot XOR ray octant), high to low, without sorting distances.
+
+struct W8Child
+{
+    Box box;
+    int inner = -1;                 // index into the W8 node list, or -1
+    std::vector<uint32_t> leaves;   // payloads when inner < 0
+};
+struct W8Node { Box box; std::vector<W8Child> ch; };
+
+struct GItem { Box box; int32_t src = -1; std::vector<uint32_t> leaves; int nested = -1; };
+
+struct CollapserW
+{
+    const std::vector<TNode>& tree;
+    int width, leaf_max;
+    std::vector<W8Node>& out;
+
+    bool all_leaf_children(const TNode& n) const
+    {
+        for(uint32_t k = 0; k < n.count; ++k) if(tree[n.first + k].count != 0) return false;
+        return true;
+    }
+    size_t opened_size(uint32_t src) const
+    {
+        const TNode& n = tree[src];
+        return all_leaf_children(n) ? (n.count + leaf_max - 1) / leaf_max : n.count;
+    }
+    void open(uint32_t src, std::vector<GItem>& items) const
+    {
+        const TNode& n = tree[src];
+        if(all_leaf_children(n))
+        {
+            const uint32_t chunks = (n.count + leaf_max - 1) / leaf_max;
+            uint32_t k = 0;
+            for(uint32_t c = 0; c < chunks; ++c)
+            {
+                uint32_t size = (n.count - k + (chunks - c) - 1) / (chunks - c);
+                GItem it; it.box.reset();
+                for(uint32_t j = 0; j < size; ++j, ++k) { it.leaves.push_back(tree[n.first + k].payload); it.box.grow(tree[n.first + k].box); }
+                items.push_back(std::move(it));
+            }
+            return;
+        }
+        for(uint32_t k = 0; k < n.count; ++k)
+        {
+            const TNode& c = tree[n.first + k];
+            GItem it; it.box = c.box;
+            if(c.count == 0) it.leaves.push_back(c.payload); else it.src = (int32_t)(n.first + k);
+            items.push_back(std::move(it));
+        }
+    }
+    // node from an explicit item list (more items than `width` are nested in consecutive groups)
+    int from_items(std::vector<GItem>& items, const Box& box)
+    {
+        if((int)items.size() > width)
+        {
+            std::vector<GItem> grouped;
+            const size_t n = items.size();
+            size_t i = 0;
+            for(int g = 0; g < width; ++g)
+            {
+                size_t end = n * (g + 1) / width;
+                if(end - i == 1) grouped.push_back(std::move(items[i]));
+                else if(end > i)
+                {
+                    std::vector<GItem> sub(std::make_move_iterator(items.begin() + i), std::make_move_iterator(items.begin() + end));
+                    Box b; b.reset(); for(auto& it : sub) b.grow(it.box);
+                    GItem it; it.box = b; it.nested = from_items(sub, b);
+                    grouped.push_back(std::move(it));
+                }
+                i = end;
+            }
+            items.swap(grouped);
+        }
+        const int self = (int)out.size();
+        out.emplace_back();
+        out[self].box = box;
+        std::vector<W8Child> ch;
+        for(auto& it : items)
+        {
+            W8Child c; c.box = it.box;
+            if(it.nested >= 0) c.inner = it.nested;
+            else if(it.src >= 0) c.inner = build((uint32_t)it.src);
+            else c.leaves = std::move(it.leaves);
+            ch.push_back(std::move(c));
+        }
+        out[self].ch = std::move(ch);
+        return self;
+    }
+    int build(uint32_t src)
+    {
+        std::vector<GItem> items;
+        open(src, items);
+        if((int)items.size() <= width)
+            for(;;)
+            {   // open the largest child while the node still has room
+                int best = -1; float best_area = -1.0f;
+                for(size_t i = 0; i < items.size(); ++i)
+                {
+                    if(items[i].src < 0) continue;
+                    if(items.size() - 1 + opened_size((uint32_t)items[i].src) > (size_t)width) continue;
+                    float a = items[i].box.area();
+                    if(a > best_area) { best_area = a; best = (int)i; }
+                }
+                if(best < 0) break;
+                uint32_t s = (uint32_t)items[best].src;
+                items.erase(items.begin() + best);
+                open(s, items);
+            }
+        return from_items(items, tree[src].box);
+    }
+};
+
+inline uint32_t f2u(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+inline float u2f(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
+
+struct CwEmitter
+{
+    const std::vector<W8Node>& w8;
+    std::vector<float4>& nodes;          // 5 per node
+    std::function<uint32_t(const std::vector<uint32_t>&)> emit_leaf; // appends leaf payloads, returns first index
+    uint32_t max_depth = 0;
+    std::string err;
+
+    // Fills node `cw` (already allocated) from w8[wi]; returns the depth below.
+    uint32_t emit(int wi, uint32_t cw)
+    {
+        const W8Node& n = w8[wi];
+        const int k = (int)n.ch.size();
+        if(k > CW_WIDTH) { err = "node wider than 8"; return 0; }
+        // greedy slot assignment: child with the best alignment to a free slot's octant direction first
+        float cx[3]; for(int a = 0; a < 3; ++a) cx[a] = 0.5f * (n.box.lo[a] + n.box.hi[a]);
+        int slot_of[CW_WIDTH]; bool slot_used[CW_WIDTH] = {false}; bool child_done[CW_WIDTH] = {false};
+        for(int it = 0; it < k; ++it)
+        {
+            float best = -FLT_MAX; int bc = -1, bs = -1;
+            for(int c = 0; c < k; ++c)
+            {
+                if(child_done[c]) continue;
+                float dx[3]; for(int a = 0; a < 3; ++a) dx[a] = 0.5f * (n.ch[c].box.lo[a] + n.ch[c].box.hi[a]) - cx[a];
+                for(int s = 0; s < CW_WIDTH; ++s)
+                {
+                    if(slot_used[s]) continue;
+                    float score = ((s & 4) ? dx[0] : -dx[0]) + ((s & 2) ? dx[1] : -dx[1]) + ((s & 1) ? dx[2] : -dx[2]);
+                    if(score > best) { best = score; bc = c; bs = s; }
+                }
+            }
+            slot_of[bc] = bs; slot_used[bs] = true; child_done[bc] = true;
+        }
+        int child_in_slot[CW_WIDTH]; for(int s = 0; s < CW_WIDTH; ++s) child_in_slot[s] = -1;
+        for(int c = 0; c < k; ++c) child_in_slot[slot_of[c]] = c;
+
+        // quantisation grid
+        int e[3]; float scale[3];
+        for(int a = 0; a < 3; ++a)
+        {
+            float ext = n.box.hi[a] - n.box.lo[a];
+            int ex = ext > 0.0f ? (int)std::ceil(std::log2((double)ext / 255.0)) : -126;
+            if(ex < -126) ex = -126;
+            // make sure 255 steps really cover the extent in float arithmetic
+            while(n.box.lo[a] + 255.0f * std::ldexp(1.0f, ex) < n.box.hi[a]) ex++;
+            if(ex > 127) { err = "box extent too large to quantise"; return 0; }
+            e[a] = ex; scale[a] = std::ldexp(1.0f, ex);
+        }
+        uint8_t qlo[3][8] = {{0}}, qhi[3][8] = {{0}}, meta[8] = {0};
+        uint32_t imask = 0, n_inner = 0;
+        for(int s = 0; s < CW_WIDTH; ++s) if(child_in_slot[s] >= 0 && n.ch[child_in_slot[s]].inner >= 0) { imask |= 1u << s; n_inner++; }
+        const uint32_t child_base = (uint32_t)(nodes.size() / 5);
+        nodes.resize(nodes.size() + 5 * (size_t)n_inner);
+        uint32_t tri_base = 0; bool have_tri_base = false; uint32_t tri_count = 0;
+        // pass 1: boxes, meta bytes and the leaf payloads (kept contiguous per node)
+        for(int s = 0; s < CW_WIDTH; ++s)
+        {
+            const int c = child_in_slot[s];
+            if(c < 0) continue;
+            const W8Child& ch = n.ch[c];
+            for(int a = 0; a < 3; ++a)
+            {
+                int lo = (int)std::floor((ch.box.lo[a] - n.box.lo[a]) / scale[a]);
+                int hi = (int)std::ceil((ch.box.hi[a] - n.box.lo[a]) / scale[a]);
+                lo = std::min(std::max(lo, 0), 255); hi = std::min(std::max(hi, 0), 255);
+                while(lo > 0 && n.box.lo[a] + (float)lo * scale[a] > ch.box.lo[a]) lo--;
+                while(hi < 255 && n.box.lo[a] + (float)hi * scale[a] < ch.box.hi[a]) hi++;
+                if(n.box.lo[a] + (float)lo * scale[a] > ch.box.lo[a] || n.box.lo[a] + (float)hi * scale[a] < ch.box.hi[a])
+                { err = "quantised box does not enclose its child"; return 0; }
+                qlo[a][s] = (uint8_t)lo; qhi[a][s] = (uint8_t)hi;
+            }
+            if(ch.inner >= 0) meta[s] = (uint8_t)((1u << 5) | (24u + (uint32_t)s));
+            else
+            {
+                const uint32_t cnt = (uint32_t)ch.leaves.size();
+                if(cnt == 0 || cnt > (uint32_t)CW_LEAF_MAX) { err = "leaf size out of range"; return 0; }
+                const uint32_t first = emit_leaf(ch.leaves);
+                if(!have_tri_base) { tri_base = first; have_tri_base = true; }
+                const uint32_t off = first - tri_base;
+                if(off != tri_count || off + cnt > 24u) { err = "leaf payloads of a node are not contiguous"; return 0; }
+                tri_count += cnt;
+                meta[s] = (uint8_t)((((1u << cnt) - 1u) << 5) | off);
+            }
+        }
+        // pass 2: inner children, stored contiguously from child_base in slot order
+        uint32_t deepest = 0, inner_rank = 0;
+        for(int s = 0; s < CW_WIDTH; ++s)
+        {
+            const int c = child_in_slot[s];
+            if(c < 0 || n.ch[c].inner < 0) continue;
+            deepest = std::max(deepest, emit(n.ch[c].inner, child_base + inner_rank));
+            if(!err.empty()) return 0;
+            inner_rank++;
+        }
+        auto pack4 = [](const uint8_t* b) { return (uint32_t)b[0] | ((uint32_t)b[1] << 8) | ((uint32_t)b[2] << 16) | ((uint32_t)b[3] << 24); };
+        float4* o = &nodes[5 * (size_t)cw];
+        const uint32_t ew = (uint32_t)(uint8_t)(int8_t)e[0] | ((uint32_t)(uint8_t)(int8_t)e[1] << 8) | ((uint32_t)(uint8_t)(int8_t)e[2] << 16) | (imask << 24);
+        o[0] = make_float4(n.box.lo[0], n.box.lo[1], n.box.lo[2], u2f(ew));
+        o[1] = make_float4(u2f(child_base), u2f(tri_base), u2f(pack4(meta)), u2f(pack4(meta + 4)));
+        o[2] = make_float4(u2f(pack4(qlo[0])), u2f(pack4(qlo[0] + 4)), u2f(pack4(qlo[1])), u2f(pack4(qlo[1] + 4)));
+        o[3] = make_float4(u2f(pack4(qlo[2])), u2f(pack4(qlo[2] + 4)), u2f(pack4(qhi[0])), u2f(pack4(qhi[0] + 4)));
+        o[4] = make_float4(u2f(pack4(qhi[1])), u2f(pack4(qhi[1] + 4)), u2f(pack4(qhi[2])), u2f(pack4(qhi[2] + 4)));
+        return deepest + 1;
+    }
+};
+
+// Builds the compressed BVH of one source tree; returns the root node index (or 0xFFFFFFFF).
+uint32_t build_cw_tree(const std::vector<TNode>& tree, int leaf_max, std::vector<float4>& nodes,
+                       const std::function<uint32_t(const std::vector<uint32_t>&)>& emit_leaf, uint32_t& depth, std::string& err)
+{
+    std::vector<W8Node> w8;
+    CollapserW col{tree, CW_WIDTH, leaf_max, w8};
+    int root;
+    if(tree[0].count == 0)
+    {   // single leaf: a node with one leaf child
+        std::vector<GItem> items(1);
+        items[0].box = tree[0].box; items[0].leaves.push_back(tree[0].payload);
+        root = col.from_items(items, tree[0].box);
+    }
+    else root = col.build(0);
+    CwEmitter em{w8, nodes, emit_leaf};
+    const uint32_t cw_root = (uint32_t)(nodes.size() / 5);
+    nodes.resize(nodes.size() + 5);
+    depth = em.emit(root, cw_root);
+    if(!em.err.empty()) { err = em.err; return 0xFFFFFFFFu; }
+    return cw_root;
+}
+
 // World-space bounds of an instance exactly as build_tlas derives them (bvh.cc:262-278):
 // the BLAS root box's eight corners through `transform`.
 void instance_world_box(const ptgpu_tlas_instance& inst, const float lo[3], const float hi[3], float out_lo[3], float out_hi[3])
@@ -366,6 +621,7 @@ bool make_wide_instance(const WideScene& ws, const ptgpu_tlas_instance& inst, ui
     out.hi = make_float4(whi[0], whi[1], whi[2], 0.0f);
     out.blas = (uint32_t)found;
     out.ref_instance = ref_index;
+    out.cw_root = (size_t)found < ws.cw_blas_root.size() ? ws.cw_blas_root[found] : 0u;
     return true;
 }
 
@@ -379,6 +635,7 @@ bool build_wide_scene(
     // 1. every BVH in the static region, in build order (= mesh load order, scene.cc:42-47)
     size_t off = 0, index_cursor = 0, vertex_cursor = 0;
     std::vector<TNode> tree;
+    uint32_t cw_blas_depth = 0;
     while(off < n_nodes)
     {
         uint32_t count = recover_tree(nodes, links, n_nodes, off, tree, err);
@@ -419,6 +676,28 @@ bool build_wide_scene(
         for(const TNode& t : tree)
             if(t.count == 0 && t.payload >= tri_count) { err = "leaf payload beyond the triangle count"; return false; }
         uint32_t stack = collapse_tree(tree, WIDE_LEAF_MAX, out.nodes, emit_leaf);
+        {   // the same tree in the compressed 8-wide layout
+            auto emit_leaf_cw = [&](const std::vector<uint32_t>& prims) -> uint32_t {
+                const uint32_t first = (uint32_t)(out.cw_tris.size() / 3);
+                for(uint32_t p : prims)
+                {
+                    const uint32_t* ix = indices + m.index_offset + 3 * (size_t)p;
+                    for(int k = 0; k < 3; ++k)
+                    {
+                        const ptgpu_float3& v = pos[m.base_vertex_offset + ix[k]];
+                        float w = 0.0f;
+                        if(k == 0) memcpy(&w, &p, 4);
+                        out.cw_tris.push_back(make_float4(v.x, v.y, v.z, w));
+                    }
+                }
+                return first;
+            };
+            uint32_t depth = 0;
+            uint32_t root = build_cw_tree(tree, CW_LEAF_MAX, out.cw_nodes, emit_leaf_cw, depth, err);
+            if(root == 0xFFFFFFFFu) { err = "compressed BVH of the BLAS at node " + std::to_string(off) + ": " + err; return false; }
+            out.cw_blas_root.push_back(root);
+            cw_blas_depth = std::max(cw_blas_depth, depth);
+        }
         wb.node_count = (uint32_t)out.nodes.size() - wb.node_offset;
         wb.tri_count = (uint32_t)(out.tris.size() / 3) - wb.tri_offset;
         if(wb.tri_count != tri_count) { err = "triangle count mismatch after collapse"; return false; }
@@ -463,6 +742,26 @@ bool build_wide_scene(
     build_sah(prims, 0, n_static, ttree, 0);
     auto emit_inst = [](const std::vector<uint32_t>& ids) -> uint32_t { return 0x80000000u | ids[0]; };
     uint32_t tstack = collapse_tree(ttree, 1, out.tlas, emit_inst);
+    {
+        auto emit_inst_cw = [&](const std::vector<uint32_t>& ids) -> uint32_t {
+            const uint32_t first = (uint32_t)out.cw_inst_index.size();
+            for(uint32_t id : ids) out.cw_inst_index.push_back(id);
+            return first;
+        };
+        uint32_t depth = 0;
+        out.cw_tlas_root = build_cw_tree(ttree, 1, out.cw_nodes, emit_inst_cw, depth, err);
+        if(out.cw_tlas_root == 0xFFFFFFFFu) { err = "compressed TLAS: " + err; return false; }
+        // per node visit at most two pushes (rest of the node group, postponed leaf group); entering an
+        // instance pushes the rest of its group and the exit marker; one entry for the dynamic instances
+        // (+2: the world-space ray constants parked under the exit marker by the wavefront kernel)
+        out.cw_max_stack = 2 * depth + 4 + 2 * cw_blas_depth + 1;
+        if(out.cw_max_stack > (uint32_t)CW_STACK)
+        {
+            err = "compressed traversal stack bound " + std::to_string(out.cw_max_stack) + " exceeds CW_STACK";
+            return false;
+        }
+        for(size_t i = 0; i < n_static; ++i) out.instances[i].cw_root = out.cw_blas_root[out.instances[i].blas];
+    }
     out.max_stack += tstack + 1 /* exit marker */ + 16 /* dynamic instances */;
     if(out.max_stack > WIDE_STACK)
     {
@@ -540,6 +839,88 @@ uint64_t verify_wide_scene(const WideScene& ws, size_t n_static, std::string& er
         }
     }
     for(size_t i = 0; i < n_static; ++i) if(inst_seen[i] != 1) { fail("static instance missing from the TLAS or duplicated"); break; }
+
+    // compressed 8-wide layout: decode every node the way the kernel does and repeat the checks
+    auto walk_cw = [&](uint32_t root, bool tlas, std::vector<uint32_t>& payload_seen, uint32_t payload_lo, uint32_t payload_hi) {
+        struct Todo { uint32_t node; Box box; bool has_box; };
+        std::vector<Todo> todo{{root, Box(), false}};
+        while(!todo.empty())
+        {
+            Todo t = todo.back(); todo.pop_back();
+            if(5 * (size_t)t.node + 4 >= ws.cw_nodes.size()) { fail("compressed child index outside the array"); continue; }
+            const float4* n = &ws.cw_nodes[5 * (size_t)t.node];
+            const uint32_t ew = f2u(n[0].w);
+            const float sc[3] = {std::ldexp(1.0f, (int)(int8_t)(ew & 0xFF)), std::ldexp(1.0f, (int)(int8_t)((ew >> 8) & 0xFF)), std::ldexp(1.0f, (int)(int8_t)((ew >> 16) & 0xFF))};
+            const float p[3] = {n[0].x, n[0].y, n[0].z};
+            const uint32_t imask = ew >> 24, child_base = f2u(n[1].x), tri_base = f2u(n[1].y);
+            const uint32_t metaw[2] = {f2u(n[1].z), f2u(n[1].w)};
+            const uint32_t q[6][2] = {{f2u(n[2].x), f2u(n[2].y)}, {f2u(n[2].z), f2u(n[2].w)}, {f2u(n[3].x), f2u(n[3].y)},
+                                      {f2u(n[3].z), f2u(n[3].w)}, {f2u(n[4].x), f2u(n[4].y)}, {f2u(n[4].z), f2u(n[4].w)}};
+            uint32_t inner_rank = 0;
+            for(int s = 0; s < 8; ++s)
+            {
+                const uint32_t meta = (metaw[s >> 2] >> (8 * (s & 3))) & 0xFF;
+                if(meta == 0) { if(imask & (1u << s)) fail("imask set on an empty slot"); continue; }
+                Box cb;
+                for(int a = 0; a < 3; ++a)
+                {
+                    cb.lo[a] = p[a] + (float)((q[a][s >> 2] >> (8 * (s & 3))) & 0xFF) * sc[a];
+                    cb.hi[a] = p[a] + (float)((q[3 + a][s >> 2] >> (8 * (s & 3))) & 0xFF) * sc[a];
+                }
+                const bool inner = (meta & 0x18) == 0x18 && (meta >> 5) == 1;
+                if(inner != ((imask >> s) & 1u)) fail("imask disagrees with meta");
+                if(inner)
+                {
+                    if((meta & 0x1F) != 24u + (uint32_t)s) fail("inner meta does not encode its slot");
+                    todo.push_back({child_base + inner_rank, cb, true});
+                    inner_rank++;
+                    continue;
+                }
+                const uint32_t bits = meta >> 5, off = meta & 0x1F;
+                const uint32_t cnt = bits == 1 ? 1 : bits == 3 ? 2 : bits == 7 ? 3 : 0;
+                if(cnt == 0) { fail("bad unary leaf count"); continue; }
+                for(uint32_t k = 0; k < cnt; ++k)
+                {
+                    const uint32_t idx = tri_base + off + k;
+                    if(tlas)
+                    {
+                        if(idx >= ws.cw_inst_index.size()) { fail("instance slot outside the list"); continue; }
+                        const uint32_t id = ws.cw_inst_index[idx];
+                        if(id >= payload_hi) fail("instance id out of range"); else payload_seen[id]++;
+                        const WideInstance& wi = ws.instances[id];
+                        const float lo[3] = {wi.lo.x, wi.lo.y, wi.lo.z}, hi[3] = {wi.hi.x, wi.hi.y, wi.hi.z};
+                        for(int a = 0; a < 3; ++a) if(lo[a] < cb.lo[a] || hi[a] > cb.hi[a]) fail("instance box outside its quantised leaf box");
+                    }
+                    else
+                    {
+                        if(idx < payload_lo || idx >= payload_hi) { fail("triangle slot outside the BLAS range"); continue; }
+                        payload_seen[idx - payload_lo]++;
+                        const float4* v = &ws.cw_tris[3 * (size_t)idx];
+                        for(int c = 0; c < 3; ++c)
+                        {
+                            const float pp[3] = {v[c].x, v[c].y, v[c].z};
+                            for(int a = 0; a < 3; ++a) if(pp[a] < cb.lo[a] || pp[a] > cb.hi[a]) fail("triangle vertex outside its quantised leaf box");
+                        }
+                    }
+                }
+            }
+        }
+    };
+    if(ws.cw_blas_root.size() != ws.blas.size()) fail("compressed BLAS table incomplete");
+    else
+    {
+        uint32_t tri_cursor = 0;
+        for(size_t b = 0; b < ws.blas.size(); ++b)
+        {
+            std::vector<uint32_t> seen(ws.blas[b].tri_count, 0);
+            walk_cw(ws.cw_blas_root[b], false, seen, tri_cursor, tri_cursor + ws.blas[b].tri_count);
+            for(uint32_t c : seen) if(c != 1) { fail("compressed BLAS " + std::to_string(b) + ": triangle missing or duplicated"); break; }
+            tri_cursor += ws.blas[b].tri_count;
+        }
+        std::vector<uint32_t> seen(n_static, 0);
+        walk_cw(ws.cw_tlas_root, true, seen, 0, (uint32_t)n_static);
+        for(uint32_t c : seen) if(c != 1) { fail("compressed TLAS: instance missing or duplicated"); break; }
+    }
     return bad;
 }
 

@@ -26,7 +26,19 @@ struct WideScene
     std::vector<WideInstance> instances; // static instances
     std::vector<WideNode> tlas;         // static TLAS
     uint32_t max_stack = 0;             // worst case over TLAS + any BLAS (+1 for the exit marker)
+
+    // compressed 8-wide layout (80-byte nodes, 8-bit child boxes, octant-ordered slots)
+    std::vector<float4> cw_nodes;       // 5 per node
+    std::vector<float4> cw_tris;        // 3 per triangle
+    std::vector<uint32_t> cw_inst_index;
+    std::vector<uint32_t> cw_blas_root; // per BLAS: root node index
+    uint32_t cw_tlas_root = 0;
+    uint32_t cw_max_stack = 0;          // group-stack entries a traversal can need
 };
+
+constexpr int CW_WIDTH = 8;             // children per node
+constexpr int CW_LEAF_MAX = 3;          // triangles per leaf child (unary count in 3 bits)
+constexpr int CW_STACK = 48;            // traversal stack entries (uint2 each, pt_cwbvh.cuh)
 
 constexpr int WIDE_LEAF_MAX = 4;        // triangles per leaf
 constexpr int WIDE_STACK = 96;          // traversal stack entries (pt_wide.cuh)

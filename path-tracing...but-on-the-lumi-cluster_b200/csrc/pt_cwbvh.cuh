@@ -1,0 +1,263 @@
+// Traversal of the compressed 8-wide BVH (layout: bvh_wide.cu, after Ylitie/Karras/Laine 2017),
+// two-level: static TLAS (leaves = instances) + per-BLAS trees, plus the subframe's few dynamic
+// instances tested directly at ray start. Replaces ray_query.hh:111-290 on the fast path.
+//
+// One node = five 16-byte loads for eight children. Child boxes are 8-bit offsets on a per-node
+// power-of-two grid and are supersets of the exact boxes, so the triangles a ray can hit are the
+// same as with the reference's boxes; the triangle test and its acceptance rule (strict
+// tmin < t < tmax) are the reference's (math.hh:340-401, ray_query.hh:245).
+// The traversal stack holds GROUPS: (base index, bit mask) of node children or of leaf payloads that
+// passed the box test, so a node visit pushes at most two entries and needs no distance sort —
+// children are stored in octant order and visited in (slot XOR ray octant) order.
+#pragma once
+#include "pt_scene.cuh"
+#include "pt_trav_links.cuh"
+#include "pt_wide.cuh"
+#include "bvh_wide.hh"
+
+namespace pt {
+
+#define CW_MARK_X 0xFFFFFFFFu
+
+struct CwState
+{
+    v3 ro, rd;          // world-space ray
+    v3 o, idir;         // current space (world or instance): origin and clamped 1/direction
+    v3 S;               // triangle-test preprocess of the instance-space direction (math.hh:340-356)
+    int axis;
+    uint32_t oct_inv4;  // ray octant, replicated in 4 bytes
+    uint32_t sign_bits; // bit0: d.x < 0, bit1: d.y < 0, bit2: d.z < 0 (current space)
+    float tmin, tmax;
+    uint2 ngroup, tgroup;
+    int sp;
+    bool in_blas, any;
+    uint32_t cur_inst, subframe;
+    Hit hit;
+};
+
+PT_D uint32_t sign_extend_s8x4(uint32_t x)
+{
+    uint32_t r;
+    asm("prmt.b32 %0, %1, 0x0, 0x0000BA98;" : "=r"(r) : "r"(x));
+    return r;
+}
+
+PT_D void cw_set_space(CwState& st, v3 o, v3 d)
+{
+    st.o = o;
+    // a zero component would give inf * 0 = NaN against the quantised grid: clamp to +-1e-20
+    const float eps = 1e-20f;
+    // MUFU.RCP (1 ulp) is enough here: the quantised child boxes carry far more slack than that
+    st.idir = mk3(__frcp_rn(fabsf(d.x) > eps ? d.x : copysignf(eps, d.x)),
+                  __frcp_rn(fabsf(d.y) > eps ? d.y : copysignf(eps, d.y)),
+                  __frcp_rn(fabsf(d.z) > eps ? d.z : copysignf(eps, d.z)));
+    st.sign_bits = (d.x < 0.0f ? 1u : 0u) | (d.y < 0.0f ? 2u : 0u) | (d.z < 0.0f ? 4u : 0u);
+    // slot bit 4 = +x side, 2 = +y, 1 = +z; a ray going +x meets the -x children first
+    const uint32_t oct = (d.x < 0.0f ? 0u : 4u) | (d.y < 0.0f ? 0u : 2u) | (d.z < 0.0f ? 0u : 1u);
+    st.oct_inv4 = oct * 0x01010101u;
+}
+
+PT_D float u8f(uint32_t w, int j) { return (float)((w >> (8 * j)) & 0xFFu); }
+
+// Box test of the eight children of one node; fills the node group (inner children hit) and the
+// leaf group (leaf payloads whose box was hit).
+PT_D void cw_intersect_node(const float4* __restrict__ nodes, uint32_t node_index, const CwState& st,
+                            uint2& ngroup, uint2& tgroup)
+{
+    const float4* n = nodes + 5 * (size_t)node_index;
+    const float4 n0 = __ldg(n), n1 = __ldg(n + 1), n2 = __ldg(n + 2), n3 = __ldg(n + 3), n4 = __ldg(n + 4);
+    const uint32_t ew = __float_as_uint(n0.w);
+    const float sx = __uint_as_float((uint32_t)(((int)(ew << 24) >> 24) + 127) << 23);
+    const float sy = __uint_as_float((uint32_t)(((int)(ew << 16) >> 24) + 127) << 23);
+    const float sz = __uint_as_float((uint32_t)(((int)(ew << 8) >> 24) + 127) << 23);
+    const float ax = sx * st.idir.x, ay = sy * st.idir.y, az = sz * st.idir.z;
+    const float ox = (n0.x - st.o.x) * st.idir.x, oy = (n0.y - st.o.y) * st.idir.y, oz = (n0.z - st.o.z) * st.idir.z;
+    const bool nx = st.sign_bits & 1u, ny = st.sign_bits & 2u, nz = st.sign_bits & 4u;
+    uint32_t hitmask = 0;
+    #pragma unroll
+    for(int half = 0; half < 2; ++half)
+    {
+        const uint32_t meta4 = __float_as_uint(half ? n1.w : n1.z);
+        const uint32_t is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
+        const uint32_t inner_mask4 = sign_extend_s8x4(is_inner4 << 3);
+        const uint32_t bit_index4 = (meta4 ^ (st.oct_inv4 & inner_mask4)) & 0x1F1F1F1Fu;
+        const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
+        const uint32_t qlx = __float_as_uint(half ? n2.y : n2.x), qly = __float_as_uint(half ? n2.w : n2.z);
+        const uint32_t qlz = __float_as_uint(half ? n3.y : n3.x), qhx = __float_as_uint(half ? n3.w : n3.z);
+        const uint32_t qhy = __float_as_uint(half ? n4.y : n4.x), qhz = __float_as_uint(half ? n4.w : n4.z);
+        const uint32_t x_near = nx ? qhx : qlx, x_far = nx ? qlx : qhx;
+        const uint32_t y_near = ny ? qhy : qly, y_far = ny ? qly : qhy;
+        const uint32_t z_near = nz ? qhz : qlz, z_far = nz ? qlz : qhz;
+        #pragma unroll
+        for(int j = 0; j < 4; ++j)
+        {
+            const float t0x = fmaf(u8f(x_near, j), ax, ox), t1x = fmaf(u8f(x_far, j), ax, ox);
+            const float t0y = fmaf(u8f(y_near, j), ay, oy), t1y = fmaf(u8f(y_far, j), ay, oy);
+            const float t0z = fmaf(u8f(z_near, j), az, oz), t1z = fmaf(u8f(z_far, j), az, oz);
+            const float cmin = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, st.tmin));
+            const float cmax = fminf(fminf(t1x, t1y), fminf(t1z, st.tmax));
+            if(cmin <= cmax)
+                hitmask |= ((child_bits4 >> (8 * j)) & 0xFFu) << ((bit_index4 >> (8 * j)) & 0xFFu);
+        }
+    }
+    ngroup.x = __float_as_uint(n1.x);
+    ngroup.y = (hitmask & 0xFF000000u) | (ew >> 24);
+    tgroup.x = __float_as_uint(n1.y);
+    tgroup.y = hitmask & 0x00FFFFFFu;
+}
+
+// Query start: the subframe's dynamic instances (world-box test) go on the stack as one instance
+// group, then the static TLAS root is the first node group.
+PT_D void cw_begin(const Scene& sc, CwState& st, uint2* stack, uint32_t subframe, v3 ro, v3 rd,
+                   float tmin, float tmax, bool any)
+{
+    st.ro = ro; st.rd = rd; st.tmin = tmin; st.tmax = tmax; st.any = any; st.subframe = subframe;
+    st.hit.t = -1.0f; st.hit.u = 0.0f; st.hit.v = 0.0f; st.hit.inst = 0xFFFFFFFFu; st.hit.prim = 0; st.hit.back_face = false;
+    st.sp = 0; st.in_blas = false; st.cur_inst = 0; st.axis = 2; st.S = mk3(0, 0, 1);
+    cw_set_space(st, ro, rd);
+    const uint2 r = __ldg(sc.dyn_range + subframe);
+    const uint32_t p = r.x, a = r.y & 0xFFFFFu, len = r.y >> 20;
+    uint32_t mask = 0;
+    for(uint32_t k = 0; k < p + len; ++k)
+    {
+        const uint32_t id = sc.n_static + (k < p ? k : a + (k - p));
+        const WideInstance* wi = sc.winst + id;
+        if(box_hit(__ldg(&wi->lo), __ldg(&wi->hi), ro, st.idir, tmin, tmax)) mask |= 1u << k;
+    }
+    if(mask) stack[st.sp++] = make_uint2(0x80000000u, mask);
+    st.ngroup = make_uint2(sc.cw_tlas_root, 0x80000000u);
+    st.tgroup = make_uint2(0u, 0u);
+}
+
+PT_D uint32_t cw_decode_instance(const Scene& sc, const CwState& st, uint32_t base, uint32_t bit)
+{
+    if(base & 0x80000000u)
+    {   // dynamic instance k of the subframe
+        const uint2 r = __ldg(sc.dyn_range + st.subframe);
+        const uint32_t p = r.x, a = r.y & 0xFFFFFu, k = (base & 0x7FFFFFFFu) + bit;
+        return sc.n_static + (k < p ? k : a + (k - p));
+    }
+    return __ldg(sc.cw_inst_index + base + bit);
+}
+
+// ray_query_enter_blas (ray_query.hh:153-182) on the compressed layout
+PT_D void cw_enter_instance(const Scene& sc, CwState& st, uint2* stack, uint32_t id)
+{
+    st.cur_inst = id;
+    const WideInstance* wi = sc.winst + id;
+    const float4 r0 = __ldg(&wi->inv0), r1 = __ldg(&wi->inv1), r2 = __ldg(&wi->inv2);
+    const uint32_t root = __ldg(&wi->cw_root);
+    const v3 o = mk3(r0.x * st.ro.x + r0.y * st.ro.y + r0.z * st.ro.z + r0.w,
+                     r1.x * st.ro.x + r1.y * st.ro.y + r1.z * st.ro.z + r1.w,
+                     r2.x * st.ro.x + r2.y * st.ro.y + r2.z * st.ro.z + r2.w);
+    const v3 d = mk3(r0.x * st.rd.x + r0.y * st.rd.y + r0.z * st.rd.z,
+                     r1.x * st.rd.x + r1.y * st.rd.y + r1.z * st.rd.z,
+                     r2.x * st.rd.x + r2.y * st.rd.y + r2.z * st.rd.z);
+    cw_set_space(st, o, d);
+    tri_preprocess(d, st.axis, st.S);
+    st.in_blas = true;
+    stack[st.sp++] = make_uint2(CW_MARK_X, 0u);
+    st.ngroup = make_uint2(root, 0x80000000u);
+    st.tgroup = make_uint2(0u, 0u);
+}
+
+// One triangle of the leaf group (ray_query_test_triangle, ray_query.hh:225-246)
+PT_D void cw_test_triangle(const Scene& sc, CwState& st, uint32_t tri)
+{
+    const float4* tp = sc.cwtris + 3 * (size_t)tri;
+    const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
+    float u, v, t; bool bf;
+    const bool ok = tri_intersect(st.o, st.axis, st.S, mk3(a), mk3(b), mk3(c), u, v, t, bf);
+    if(ok && t < st.tmax && t > st.tmin)
+    {
+        st.hit.t = t; st.hit.u = u; st.hit.v = v; st.hit.inst = st.cur_inst; st.hit.prim = __float_as_uint(a.w); st.hit.back_face = bf;
+        st.tmax = t;
+        if(st.any) { st.sp = 0; st.ngroup.y = 0u; st.tgroup.y = 0u; }
+    }
+}
+
+// node phase: take the next child of the node group (highest bit = nearest in octant order), test it
+PT_D void cw_node_phase(const Scene& sc, CwState& st, uint2* stack)
+{
+    if(st.ngroup.y > 0x00FFFFFFu)
+    {
+        const uint32_t hits_imask = st.ngroup.y;
+        const uint32_t child_bit = 31u - (uint32_t)__clz(hits_imask);
+        const uint32_t base = st.ngroup.x;
+        st.ngroup.y &= ~(1u << child_bit);
+        if(st.ngroup.y > 0x00FFFFFFu) stack[st.sp++] = st.ngroup;
+        const uint32_t slot = (child_bit - 24u) ^ (st.oct_inv4 & 0xFFu);
+        const uint32_t rel = (uint32_t)__popc(hits_imask & ~(0xFFFFFFFFu << slot));
+        cw_intersect_node(sc.cwnodes, base + rel, st, st.ngroup, st.tgroup);
+    }
+    else
+    {   // the entry popped last was a leaf group
+        st.tgroup = st.ngroup;
+        st.ngroup = make_uint2(0u, 0u);
+    }
+}
+
+// instance phase (TLAS context): enter one instance of the leaf group, park everything else
+PT_D void cw_instance_phase(const Scene& sc, CwState& st, uint2* stack)
+{
+    const uint32_t bit = 31u - (uint32_t)__clz(st.tgroup.y);
+    st.tgroup.y &= ~(1u << bit);
+    if(st.ngroup.y > 0x00FFFFFFu) stack[st.sp++] = st.ngroup;
+    if(st.tgroup.y) stack[st.sp++] = st.tgroup;
+    cw_enter_instance(sc, st, stack, cw_decode_instance(sc, st, st.tgroup.x, bit));
+}
+
+// pop phase; returns false when the query is complete
+PT_D bool cw_pop_phase(CwState& st, uint2* stack)
+{
+    if(st.ngroup.y <= 0x00FFFFFFu)
+    {
+        if(st.sp == 0) return false;
+        const uint2 e = stack[--st.sp];
+        if(e.y == 0u)
+        {   // exit marker: BLAS finished, back to world space
+            st.in_blas = false;
+            cw_set_space(st, st.ro, st.rd);
+            st.ngroup = make_uint2(0u, 0u);
+        }
+        else st.ngroup = e;
+    }
+    return true;
+}
+
+template<bool ANY>
+PT_D bool trace_cw(const Scene& sc, uint32_t subframe, v3 origin, v3 dir, float tmin, float tmax, Hit& hit)
+{
+    uint2 stack[CW_STACK];
+    CwState st;
+    cw_begin(sc, st, stack, subframe, origin, dir, tmin, tmax, ANY);
+    for(;;)
+    {
+        cw_node_phase(sc, st, stack);
+        if(st.in_blas)
+        {
+            while(st.tgroup.y)
+            {
+                const uint32_t bit = 31u - (uint32_t)__clz(st.tgroup.y);
+                st.tgroup.y &= ~(1u << bit);
+                cw_test_triangle(sc, st, st.tgroup.x + bit);
+            }
+        }
+        else if(st.tgroup.y) cw_instance_phase(sc, st, stack);
+        if(!cw_pop_phase(st, stack)) break;
+    }
+    hit = st.hit;
+    return ANY ? hit.t >= 0.0f : hit.t >= 0.0f;
+}
+
+struct CwTrav
+{
+    template<bool ANY>
+    static PT_D bool trace(const Scene& sc, const SubframeCtx& sf, v3 o, v3 d, float tmin, float tmax,
+                           Hit& h, TravCounters&)
+    {
+        return trace_cw<ANY>(sc, sf.index, o, d, tmin, tmax, h);
+    }
+};
+
+} // namespace pt

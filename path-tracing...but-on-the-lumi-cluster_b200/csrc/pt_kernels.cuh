@@ -14,7 +14,10 @@ struct RenderJob
     uchar4* out_bgra;      // w*h BGRA (tonemap_pixel), row 0 = top, or null
     uint8_t* out_bmp;      // full BMP file image (bmp.cc:15-52) for a full-frame job, or null
     uint32_t bmp_pitch;
-    int32_t min_active;    // megakernel: leave the traversal loop when fewer lanes than this still traverse
+    int32_t min_active;    // megakernel: leave the traversal loop when fewer lanes than this still traverse;
+                           // wavefront: idle lanes needed before a warp refills from the ray queue
+    int32_t tri_threshold, xform_threshold; // wavefront/compressed: lanes needed to elect the triangle / space-change block
+    int32_t node_threshold, node_burst;     // wavefront/compressed: lanes needed to continue a node burst, and its length
 };
 
 constexpr int TILE_W = 8, TILE_H = 4, SAMPLE_LANES = 8;

@@ -67,7 +67,8 @@ struct WideInstance
     float4 lo, hi;            // world-space AABB of the instance (as build_tlas computes, bvh.cc:262-278)
     uint32_t blas;            // index into WideBlas
     uint32_t ref_instance;    // index into the reference instance array (for shading)
-    uint32_t pad[10];
+    uint32_t cw_root;         // root node of the instance's BLAS in the compressed 8-wide array
+    uint32_t pad[9];
 };
 static_assert(sizeof(WideInstance) == 128, "wide instance");
 
@@ -89,7 +90,12 @@ struct Scene
     const WideBlas* wblas;
     const WideInstance* winst;      // parallel to `instances`
     const WideNode* wtlas;          // static TLAS over static instances (leaf slot = instance index)
-    const uint2* dyn_range;         // per subframe: [begin,end) into instances (dynamic part)
+    const uint2* dyn_range;         // per subframe: dynamic instance set {prefix p, a | len << 20} (ptgpu_api.cu)
+    // compressed 8-wide layout (bvh_wide.cu: build_cw_*, pt_cwbvh.cuh)
+    const float4* cwnodes;          // 5 float4 (80 B) per node, all BLASes then the static TLAS
+    const float4* cwtris;           // 3 float4 per triangle, leaf order; p0.w = primitive id (bits)
+    const uint32_t* cw_inst_index;  // TLAS leaf order -> instance index
+    uint32_t cw_tlas_root;
     uint32_t n_static;
     uint32_t n_subframes;
     // config

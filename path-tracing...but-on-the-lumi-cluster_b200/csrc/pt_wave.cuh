@@ -15,6 +15,7 @@
 #pragma once
 #include "pt_kernels.cuh"
 #include "pt_wide.cuh"
+#include "pt_cwbvh.cuh"
 
 namespace pt {
 
@@ -348,6 +349,240 @@ wf_trace_kernel(Scene sc, RenderJob job, WaveBuffers wb)
     }
     // pad the partly filled output chunks so that consumers can skip them (fill == 32 with no
     // reservation is the initial state, so only chunks with fill < 32 exist and need padding)
+    if(near_fill < 32u && near_fill + lane < 32u) wb.q_near[near_base + near_fill + lane] = WF_INVALID;
+    if(far_fill < 32u && far_fill + lane < 32u) wb.q_far[far_base + far_fill + lane] = WF_INVALID;
+}
+
+// ---- trace on the compressed 8-wide BVH (pt_cwbvh.cuh): same queue protocol as wf_trace_kernel ------
+//
+// Scheduling inside a warp (each decision backed by an ncu source-level profile, profiles/):
+//   * one code block per iteration, elected by ballot: NODE (box tests of one 8-wide node), TRI (one
+//     triangle test per lane) or ENTER (transform the ray into an instance);
+//   * leaf groups found by NODE go to a small per-lane pending list, so a lane keeps descending while
+//     its triangles wait for the TRI block to be worth running (>= tri_threshold lanes): unvoted, the
+//     triangle test ran with 2.5 of 32 lanes and was 37 % of all issued instructions;
+//   * leaving an instance is free: the world-space ray constants are parked under the exit marker;
+//   * a lane whose query ends takes the next ray from the global queue (refill when >= min_active
+//     lanes are idle), closest-hit and shadow rays alike.
+constexpr int CW_PEND = 4;
+
+#ifndef WF_CW_BLOCKS
+#define WF_CW_BLOCKS 8
+#endif
+__global__ void __launch_bounds__(WF_TRACE_THREADS, WF_CW_BLOCKS)
+wf_trace_cw_kernel(Scene sc, RenderJob job, WaveBuffers wb)
+{
+    const unsigned lane = threadIdx.x & 31u;
+    const uint32_t n_entries = wb.cnt->n_trace;
+    uint32_t res_base = 0, res_n = 0;
+    bool exhausted = false;
+    uint32_t far_base = 0, far_fill = 32, near_base = 0, near_fill = 32;
+
+    bool active = false;
+    int done_class = 0;
+    uint32_t slot = 0;
+    uint2 stack[CW_STACK];
+    uint2 pend[CW_PEND];
+    int np = 0;
+    CwState st;
+    st.ngroup = make_uint2(0u, 0u); st.tgroup = make_uint2(0u, 0u); st.sp = 0; st.in_blas = false; st.any = false;
+
+    for(;;)
+    {
+        const unsigned act = __ballot_sync(0xFFFFFFFFu, active);
+        if(32 - __popc(act) >= job.min_active || act == 0u)
+        {
+            // -- queue finished closest-hit queries by class, in 32-entry chunks per warp --------------
+            #pragma unroll
+            for(int cls = 1; cls <= 2; ++cls)
+            {
+                const unsigned m = __ballot_sync(0xFFFFFFFFu, done_class == cls);
+                if(m == 0u) continue;
+                uint32_t& base = cls == 1 ? near_base : far_base;
+                uint32_t& fill = cls == 1 ? near_fill : far_fill;
+                uint32_t* q = cls == 1 ? wb.q_near : wb.q_far;
+                uint32_t* qn = cls == 1 ? &wb.cnt->n_near : &wb.cnt->n_far;
+                const uint32_t cnt = (uint32_t)__popc(m);
+                const uint32_t rank = (uint32_t)__popc(m & ((1u << lane) - 1u));
+                const uint32_t room = 32u - fill;
+                uint32_t new_base = 0;
+                if(cnt > room)
+                {
+                    if(lane == 0) new_base = atomicAdd(qn, 32u);
+                    new_base = __shfl_sync(0xFFFFFFFFu, new_base, 0);
+                }
+                if(done_class == cls)
+                {
+                    if(rank < room) q[base + fill + rank] = slot;
+                    else q[new_base + (rank - room)] = slot;
+                    done_class = 0;
+                }
+                if(cnt > room) { base = new_base; fill = cnt - room; }
+                else fill += cnt;
+            }
+            // -- refill idle lanes from the ray queue ------------------------------------------------
+            const unsigned idle = ~act;
+            const uint32_t want = (uint32_t)__popc(idle);
+            const uint32_t my_rank = (uint32_t)__popc(idle & ((1u << lane) - 1u));
+            uint32_t entry_index = WF_INVALID;
+            uint32_t served = 0;
+            while(want > served && !(exhausted && res_n == 0u))
+            {
+                if(res_n == 0u)
+                {
+                    uint32_t b = 0;
+                    if(lane == 0) b = atomicAdd(&wb.cnt->cur_trace, (uint32_t)WF_FETCH_CHUNK);
+                    b = __shfl_sync(0xFFFFFFFFu, b, 0);
+                    if(b >= n_entries) { exhausted = true; break; }
+                    res_base = b;
+                    res_n = min((uint32_t)WF_FETCH_CHUNK, n_entries - b);
+                }
+                const uint32_t take = min(res_n, want - served);
+                if(!active && my_rank >= served && my_rank < served + take) entry_index = res_base + (my_rank - served);
+                res_base += take; res_n -= take; served += take;
+            }
+            if(entry_index != WF_INVALID)
+            {
+                const uint32_t e = __ldg(wb.q_trace + entry_index);
+                if(e != WF_INVALID)
+                {
+                    slot = e & ~WF_SHADOW_BIT;
+                    const bool shadow = (e & WF_SHADOW_BIT) != 0u;
+                    const float4 fo = wb.ray_o[slot];
+                    const float4 fd = shadow ? wb.shadow_d[slot] : wb.ray_d[slot];
+                    const int sample = job.s_begin + wb.cursor[slot].x * job.s_stride;
+                    const uint32_t subframe = sample < 0 ? 0u : (uint32_t)sample / (uint32_t)sc.samples_per_subframe;
+                    cw_begin(sc, st, stack, subframe, mk3(fo.x, fo.y, fo.z), mk3(fd.x, fd.y, fd.z), fo.w, PT_MAX_RAY_DIST, shadow);
+                    np = 0;
+                    active = true;
+                }
+            }
+            if(__ballot_sync(0xFFFFFFFFu, active) == 0u)
+            {
+                if(exhausted && res_n == 0u) break;
+                continue;
+            }
+        }
+
+        // The three code blocks as lambdas; each is executed by the lanes that want it, in bursts.
+        auto advance = [&]() {
+            // a lane with neither node children nor a leaf group pops (cheap, unvoted)
+            if(active && st.ngroup.y <= 0x00FFFFFFu && st.tgroup.y == 0u)
+            {
+                if(st.sp == 0)
+                {
+                    if(np == 0)
+                    {   // query complete: write the result
+                        active = false;
+                        if(st.any) wb.visible[slot] = st.hit.t < 0.0f ? 1u : 0u;
+                        else
+                        {
+                            wb.hit[slot] = make_float4(st.hit.t, st.hit.u, st.hit.v, __uint_as_float(st.hit.inst));
+                            wb.hit_prim[slot] = st.hit.prim | (st.hit.back_face ? 0x80000000u : 0u);
+                            done_class = (st.hit.t > 0.0f && st.hit.t < 1e3f) ? 1 : 2;
+                        }
+                    }
+                }
+                else
+                {
+                    const uint2 e = stack[st.sp - 1];
+                    if(e.y == 0u)
+                    {   // exit marker: leave the instance once its pending triangles are done
+                        if(np == 0)
+                        {
+                            st.sp -= 3;
+                            const uint2 a = stack[st.sp], b = stack[st.sp + 1];
+                            st.o = st.ro;
+                            st.idir = mk3(__uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(b.x));
+                            st.oct_inv4 = (b.y & 0xFFu) * 0x01010101u;
+                            st.sign_bits = (b.y >> 8) & 7u;
+                            st.in_blas = false;
+                        }
+                    }
+                    else
+                    {
+                        st.sp--;
+                        if(e.y > 0x00FFFFFFu) st.ngroup = e; else st.tgroup = e;
+                    }
+                }
+            }
+        };
+        auto wants_node = [&]() { return active && st.ngroup.y > 0x00FFFFFFu && np < CW_PEND && !(!st.in_blas && st.tgroup.y != 0u); };
+        auto wants_tri = [&]() { return active && np > 0; };
+        auto wants_enter = [&]() { return active && !st.in_blas && st.tgroup.y != 0u; };
+        auto node_step = [&]() {
+            cw_node_phase(sc, st, stack);
+            if(st.tgroup.y != 0u)
+            {
+                if(st.in_blas) { pend[np++] = st.tgroup; st.tgroup.y = 0u; }              // triangles wait for the TRI block
+                else if(st.ngroup.y > 0x00FFFFFFu) { stack[st.sp++] = st.tgroup; st.tgroup.y = 0u; } // instances wait below the TLAS nodes
+            }
+        };
+        auto tri_step = [&]() {
+            // one triangle of the newest pending leaf group
+            uint2 g = pend[np - 1];
+            const uint32_t bit = 31u - (uint32_t)__clz(g.y);
+            g.y &= ~(1u << bit);
+            if(g.y) pend[np - 1] = g; else np--;
+            cw_test_triangle(sc, st, g.x + bit);
+            if(st.any && st.hit.t >= 0.0f) np = 0; // any hit ends a shadow query (sp and groups are cleared)
+        };
+        auto enter_step = [&]() {
+            // enter one instance of the group; the rest of the group and the world-space ray constants are
+            // parked under the exit marker, which makes leaving the instance a few loads
+            const uint32_t bit = 31u - (uint32_t)__clz(st.tgroup.y);
+            st.tgroup.y &= ~(1u << bit);
+            if(st.tgroup.y) stack[st.sp++] = st.tgroup;
+            stack[st.sp++] = make_uint2(__float_as_uint(st.idir.x), __float_as_uint(st.idir.y));
+            stack[st.sp++] = make_uint2(__float_as_uint(st.idir.z), (st.oct_inv4 & 0xFFu) | (st.sign_bits << 8));
+            cw_enter_instance(sc, st, stack, cw_decode_instance(sc, st, st.tgroup.x, bit));
+        };
+
+        bool progress = false;
+        // -- NODE burst: while enough lanes have node children, nothing else is looked at --------------
+        #pragma unroll 1
+        for(int b = 0; b < job.node_burst; ++b)
+        {
+            advance();
+            const bool w = wants_node();
+            if(__popc(__ballot_sync(0xFFFFFFFFu, w)) < job.node_threshold) break;
+            if(w) node_step();
+            progress = true;
+        }
+        // -- TRI block: worth running once enough lanes hold pending triangles ---------------------------
+        {
+            bool w = wants_tri();
+            int n = __popc(__ballot_sync(0xFFFFFFFFu, w));
+            #pragma unroll 1
+            for(int b = 0; b < 3 && n >= job.tri_threshold; ++b)
+            {
+                if(w) tri_step();
+                progress = true;
+                w = wants_tri();
+                n = __popc(__ballot_sync(0xFFFFFFFFu, w));
+            }
+        }
+        // -- ENTER block -----------------------------------------------------------------------------------
+        {
+            advance();
+            const bool w = wants_enter();
+            if(__popc(__ballot_sync(0xFFFFFFFFu, w)) >= job.xform_threshold)
+            {
+                if(w) enter_step();
+                progress = true;
+            }
+        }
+        if(!progress)
+        {   // no block met its threshold: run the fullest one once so that every lane eventually advances
+            const bool wn = wants_node(), wt = wants_tri(), we = wants_enter();
+            const int nn = __popc(__ballot_sync(0xFFFFFFFFu, wn));
+            const int nt = __popc(__ballot_sync(0xFFFFFFFFu, wt));
+            const int ne = __popc(__ballot_sync(0xFFFFFFFFu, we));
+            if(nn >= nt && nn >= ne) { if(wn) node_step(); }
+            else if(nt >= ne) { if(wt) tri_step(); }
+            else { if(we) enter_step(); }
+        }
+    }
     if(near_fill < 32u && near_fill + lane < 32u) wb.q_near[near_base + near_fill + lane] = WF_INVALID;
     if(far_fill < 32u && far_fill + lane < 32u) wb.q_far[far_base + far_fill + lane] = WF_INVALID;
 }

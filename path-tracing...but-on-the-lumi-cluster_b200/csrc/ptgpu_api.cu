@@ -4,6 +4,7 @@
 #include "pt_wide.cuh"
 #include "pt_mega.cuh"
 #include "pt_wave.cuh"
+#include "pt_cwbvh.cuh"
 #include "bvh_wide.hh"
 
 #include <cstdarg>
@@ -59,6 +60,8 @@ struct ptgpu_ctx
     int counters_on = 0;
     int kernel = 2;    // 0 megakernel, 1 simple tiles, 2 wavefront
     int min_active = -1; // -1: per-kernel default
+    int bvh = 1;         // 0: 4-wide float BVH, 1: compressed 8-wide BVH
+    int tri_threshold = 8, xform_threshold = 4, node_threshold = 12, node_burst = 2;
 
     // static scene, reference layout
     DevBuf<float2> ref_nodes;     // 3 per node; static region then per-frame TLAS region
@@ -78,6 +81,8 @@ struct ptgpu_ctx
     DevBuf<WideInstance> winst;     // static + dynamic
     DevBuf<WideNode> wtlas;
     size_t n_wtlas = 0;
+    DevBuf<float4> cwnodes, cwtris;
+    DevBuf<uint32_t> cw_inst_index;
 
     // per frame
     DevBuf<RefSubframe> subframes;
@@ -150,6 +155,8 @@ Scene make_scene(ptgpu_ctx* ctx)
     s.subframes = ctx->subframes.p;
     s.wnodes = ctx->wnodes.p; s.wtris = ctx->wtris.p; s.wblas = ctx->wblas.p; s.winst = ctx->winst.p;
     s.wtlas = ctx->wtlas.p; s.dyn_range = ctx->dyn_range.p;
+    s.cwnodes = ctx->cwnodes.p; s.cwtris = ctx->cwtris.p; s.cw_inst_index = ctx->cw_inst_index.p;
+    s.cw_tlas_root = ctx->wide_host.cw_tlas_root;
     s.n_static = (uint32_t)ctx->n_static;
     s.n_subframes = (uint32_t)ctx->n_subframes;
     s.width = ctx->cfg.width; s.height = ctx->cfg.height;
@@ -200,6 +207,8 @@ int launch_wave(ptgpu_ctx* ctx, const Scene& sc, RenderJob job)
     wb.q_new = (uint32_t*)(m + o_qw); wb.cnt = (WaveCounters*)(m + o_cnt);
     wb.n_slots = n_slots; wb.tiles_x = tiles_x;
     if(job.min_active < 1) job.min_active = 1;
+    job.tri_threshold = ctx->tri_threshold; job.xform_threshold = ctx->xform_threshold;
+    job.node_threshold = ctx->node_threshold; job.node_burst = ctx->node_burst;
 
     cudaStream_t st = ctx->stream;
     int launches = 0;
@@ -215,7 +224,8 @@ int launch_wave(ptgpu_ctx* ctx, const Scene& sc, RenderJob job)
         for(int b = 0; b < check_every && rounds < max_rounds; ++b, ++rounds)
         {
             wf_generate_kernel<<<sms * 4, 256, 0, st>>>(sc, job, wb);
-            wf_trace_kernel<<<sms * 6, WF_TRACE_THREADS, 0, st>>>(sc, job, wb);
+            if(ctx->bvh == 1) wf_trace_cw_kernel<<<sms * WF_CW_BLOCKS, WF_TRACE_THREADS, 0, st>>>(sc, job, wb);
+            else wf_trace_kernel<<<sms * 6, WF_TRACE_THREADS, 0, st>>>(sc, job, wb);
             wf_phase_kernel<<<1, 32, 0, st>>>(wb, 1, nullptr);
             wf_shade_kernel<true><<<sms * 8, 128, 0, st>>>(sc, job, wb);
             wf_shade_kernel<false><<<sms * 8, 128, 0, st>>>(sc, job, wb);
@@ -374,7 +384,7 @@ void ptgpu_destroy(ptgpu_ctx* ctx)
     ctx->ref_nodes.release(); ctx->ref_links.release(); ctx->indices.release();
     ctx->pos.release(); ctx->normal.release(); ctx->albedo.release(); ctx->material.release();
     ctx->instances.release(); ctx->wnodes.release(); ctx->wtris.release(); ctx->wblas.release();
-    ctx->winst.release(); ctx->wtlas.release(); ctx->subframes.release(); ctx->dyn_range.release();
+    ctx->winst.release(); ctx->wtlas.release(); ctx->cwnodes.release(); ctx->cwtris.release(); ctx->cw_inst_index.release(); ctx->subframes.release(); ctx->dyn_range.release();
     ctx->out_bgra.release(); ctx->out_bmp.release(); ctx->out_rgb.release(); ctx->counters.release();
     ctx->mega_state.release(); ctx->wave_mem.release(); ctx->wave_flag.release();
     if(ctx->wave_flag_host) cudaFreeHost(ctx->wave_flag_host);
@@ -440,6 +450,12 @@ int ptgpu_upload_static(
     CK(cudaMemcpy(ctx->winst.p, w.instances.data(), n_static * sizeof(WideInstance), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(ctx->wtlas.p, w.tlas.data(), w.tlas.size() * sizeof(WideNode), cudaMemcpyHostToDevice));
     ctx->n_wtlas = w.tlas.size();
+    CK(ctx->cwnodes.reserve(w.cw_nodes.size()));
+    CK(ctx->cwtris.reserve(w.cw_tris.size()));
+    CK(ctx->cw_inst_index.reserve(w.cw_inst_index.size()));
+    CK(cudaMemcpy(ctx->cwnodes.p, w.cw_nodes.data(), w.cw_nodes.size() * sizeof(float4), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->cwtris.p, w.cw_tris.data(), w.cw_tris.size() * sizeof(float4), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->cw_inst_index.p, w.cw_inst_index.data(), w.cw_inst_index.size() * 4, cudaMemcpyHostToDevice));
     ctx->have_static = true;
     ctx->have_frame = false;
     return 0;
@@ -559,7 +575,7 @@ static int render_full(ptgpu_ctx* ctx, bool bgra, bool bmp)
     job.out_bgra = bgra ? ctx->out_bgra.p : nullptr;
     job.out_bmp = bmp ? ctx->out_bmp.p : nullptr;
     job.bmp_pitch = ctx->bmp_pitch;
-    job.min_active = ctx->min_active < 0 ? (ctx->kernel == 2 ? 1 : 0) : ctx->min_active;
+    job.min_active = ctx->min_active < 0 ? (ctx->kernel == 2 ? 8 : 0) : ctx->min_active;
     int launches = 0;
     CK(cudaEventRecord(ctx->ev_begin, ctx->stream));
     if(bmp && !ctx->bmp_header_done)
@@ -674,7 +690,7 @@ int ptgpu_render_rect(
     job.x0 = x0; job.y0 = y0; job.w = w; job.h = h;
     job.s_begin = s_begin; job.s_count = s_count; job.s_stride = s_stride;
     job.out_rgb = ctx->out_rgb.p; job.out_bgra = d_bgra; job.out_bmp = nullptr; job.bmp_pitch = 0;
-    job.min_active = ctx->min_active < 0 ? (ctx->kernel == 2 ? 1 : 0) : ctx->min_active;
+    job.min_active = ctx->min_active < 0 ? (ctx->kernel == 2 ? 8 : 0) : ctx->min_active;
     CK(cudaEventRecord(ctx->ev_begin, ctx->stream));
     int l = launch_job(ctx, job);
     if(l < 0) { tmp_bgra.release(); return fail(ctx, "kernel launch failed: %s", cudaGetErrorString(cudaGetLastError())); }
@@ -704,6 +720,8 @@ int ptgpu_trace_samples(ptgpu_ctx* ctx, const uint32_t* xy, const int32_t* sampl
     const int threads = 128; const int blocks = (int)((n + threads - 1) / threads);
     if(ctx->traversal == 1)
         trace_samples_kernel<LinksTrav<false>><<<blocks, threads, 0, ctx->stream>>>(sc, (uint32_t*)ctx->scratch_a.p, (int32_t*)ctx->scratch_b.p, n, (float*)ctx->scratch_c.p);
+    else if(ctx->bvh == 1)
+        trace_samples_kernel<CwTrav><<<blocks, threads, 0, ctx->stream>>>(sc, (uint32_t*)ctx->scratch_a.p, (int32_t*)ctx->scratch_b.p, n, (float*)ctx->scratch_c.p);
     else
         trace_samples_kernel<WideTrav><<<blocks, threads, 0, ctx->stream>>>(sc, (uint32_t*)ctx->scratch_a.p, (int32_t*)ctx->scratch_b.p, n, (float*)ctx->scratch_c.p);
     CK(cudaGetLastError());
@@ -740,6 +758,8 @@ int ptgpu_trace_closest(ptgpu_ctx* ctx, const float* rays, size_t n, uint32_t su
     const int threads = 128; const int blocks = (int)((n + threads - 1) / threads);
     if(ctx->traversal == 1)
         trace_closest_kernel<LinksTrav<false>><<<blocks, threads, 0, ctx->stream>>>(sc, (float*)ctx->scratch_a.p, n, subframe, (float*)ctx->scratch_b.p, (uint32_t*)ctx->scratch_c.p);
+    else if(ctx->bvh == 1)
+        trace_closest_kernel<CwTrav><<<blocks, threads, 0, ctx->stream>>>(sc, (float*)ctx->scratch_a.p, n, subframe, (float*)ctx->scratch_b.p, (uint32_t*)ctx->scratch_c.p);
     else
         trace_closest_kernel<WideTrav><<<blocks, threads, 0, ctx->stream>>>(sc, (float*)ctx->scratch_a.p, n, subframe, (float*)ctx->scratch_b.p, (uint32_t*)ctx->scratch_c.p);
     CK(cudaGetLastError());
@@ -770,6 +790,11 @@ int ptgpu_set_option(ptgpu_ctx* ctx, const char* key, int64_t value)
     if(!strcmp(key, "traversal")) { if(value != 0 && value != 1) return fail(ctx, "traversal must be 0 or 1"); ctx->traversal = (int)value; ctx->have_frame = false; return 0; }
     if(!strcmp(key, "counters")) { ctx->counters_on = value != 0; return 0; }
     if(!strcmp(key, "kernel")) { if(value < 0 || value > 2) return fail(ctx, "kernel must be 0, 1 or 2"); ctx->kernel = (int)value; return 0; }
+    if(!strcmp(key, "bvh")) { if(value != 0 && value != 1) return fail(ctx, "bvh must be 0 or 1"); ctx->bvh = (int)value; return 0; }
+    if(!strcmp(key, "tri_threshold")) { if(value < 1 || value > 32) return fail(ctx, "tri_threshold must be 1..32"); ctx->tri_threshold = (int)value; return 0; }
+    if(!strcmp(key, "xform_threshold")) { if(value < 1 || value > 32) return fail(ctx, "xform_threshold must be 1..32"); ctx->xform_threshold = (int)value; return 0; }
+    if(!strcmp(key, "node_threshold")) { if(value < 1 || value > 32) return fail(ctx, "node_threshold must be 1..32"); ctx->node_threshold = (int)value; return 0; }
+    if(!strcmp(key, "node_burst")) { if(value < 1 || value > 64) return fail(ctx, "node_burst must be 1..64"); ctx->node_burst = (int)value; return 0; }
     if(!strcmp(key, "min_active")) { if(value < -1 || value > 32) return fail(ctx, "min_active must be -1..32"); ctx->min_active = (int)value; return 0; }
     return fail(ctx, "unknown option '%s'", key);
 }
@@ -817,7 +842,7 @@ int ptgpu_host_flatten_check(
     {
         uint64_t bad = verify_wide_scene(ws, n_static, e);
         out[0] = ws.blas.size(); out[1] = ws.nodes.size(); out[2] = ws.tris.size() / 3; out[3] = ws.tlas.size();
-        out[4] = ws.max_stack; out[5] = bad; out[6] = WIDE_STACK; out[7] = 0;
+        out[4] = ws.max_stack; out[5] = bad; out[6] = WIDE_STACK; out[7] = ws.cw_nodes.size() / 5;
         if(bad == 0) return 0;
     }
     if(err && err_len) { strncpy(err, e.c_str(), err_len - 1); err[err_len - 1] = 0; }

@@ -15,10 +15,11 @@ def main():
     cfg = pkg.Config.testing()
     r = pkg.Renderer(cfg, 0)
     r.upload_static(**sio.load_static(sio.static_path()))
-    variants = [("mega/0", {"kernel": 0, "min_active": 0}), ("wave/1", {"kernel": 2, "min_active": 1}),
-                ("wave/4", {"kernel": 2, "min_active": 4}), ("wave/8", {"kernel": 2, "min_active": 8}),
-                ("wave/16", {"kernel": 2, "min_active": 16})]
+    variants = []
+    for nt, nb, tt, xt in ((12, 4, 8, 4), (16, 4, 8, 4), (8, 4, 8, 4), (12, 8, 8, 4), (12, 2, 8, 4), (12, 4, 12, 4), (12, 4, 6, 2), (16, 8, 12, 6)):
+        variants.append(("cw n%d b%d t%d x%d" % (nt, nb, tt, xt), {"kernel": 2, "bvh": 1, "min_active": 8, "node_threshold": nt, "node_burst": nb, "tri_threshold": tt, "xform_threshold": xt}))
     try:
+        if os.environ.get("PTGPU_NO_ORACLE"): raise RuntimeError()
         from oracle import refbind
         o = refbind.get("fast"); o.load_scene()
     except Exception as e:  # noqa
