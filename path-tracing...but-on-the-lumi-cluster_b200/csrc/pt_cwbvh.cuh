@@ -168,9 +168,17 @@ PT_D void cw_test_triangle(const Scene& sc, CwState& st, uint32_t tri)
     const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
     float u, v, t; bool bf;
     const bool ok = tri_intersect(st.o, st.axis, st.S, mk3(a), mk3(b), mk3(c), u, v, t, bf);
-    if(ok && t < st.tmax && t > st.tmin)
+    // The reference accepts strictly closer candidates, so among exactly tied hits (a ray through a
+    // shared edge) the first one ITS traversal order finds wins (ray_query.hh:245,289). This kernel
+    // tests triangles in an order that depends on warp scheduling, so ties are broken by the smallest
+    // (instance, primitive) instead: deterministic and independent of traversal order.
+    const uint32_t prim = __float_as_uint(a.w);
+    const bool closer = t < st.tmax;
+    const bool tie = st.hit.t >= 0.0f && t == st.hit.t &&
+        (st.cur_inst < st.hit.inst || (st.cur_inst == st.hit.inst && prim < st.hit.prim));
+    if(ok && t > st.tmin && (closer || tie))
     {
-        st.hit.t = t; st.hit.u = u; st.hit.v = v; st.hit.inst = st.cur_inst; st.hit.prim = __float_as_uint(a.w); st.hit.back_face = bf;
+        st.hit.t = t; st.hit.u = u; st.hit.v = v; st.hit.inst = st.cur_inst; st.hit.prim = prim; st.hit.back_face = bf;
         st.tmax = t;
         if(st.any) { st.sp = 0; st.ngroup.y = 0u; st.tgroup.y = 0u; }
     }

@@ -21,13 +21,18 @@ namespace pt {
 
 #define WF_INVALID 0xFFFFFFFFu
 #define WF_SHADOW_BIT 0x80000000u
+#define WF_SEG_BOUNCE 0
+#define WF_SEG_PRIMARY 1
+#define WF_SEG_SHADOW 2
+#define WF_NEED_SAMPLE (-1)   // cursor.y: the slot waits for wf_generate
+#define WF_FINISHED (-2)      // cursor.y: no samples left
 
 struct WaveCounters
 {
-    uint32_t n_trace, n_far, n_near, n_new;   // queue extents
-    uint32_t cur_trace;                       // fetch cursor of wf_trace
-    uint32_t active_slots;                    // slots that still have samples to trace
-    uint32_t pad[2];
+    uint32_t n_seg[3];                        // ray-queue segment extents: 0 bounce, 1 primary, 2 shadow
+    uint32_t n_far, n_near, n_new;            // result-queue extents; slots waiting for their next sample
+    uint32_t cur_trace;                       // fetch cursor of wf_trace over the concatenated segments
+    uint32_t pad;
 };
 
 struct WaveBuffers
@@ -46,12 +51,14 @@ struct WaveBuffers
     int2* cursor;         // x = k (index into the sample set), y = bounce
     uint32_t* visible;    // shadow query result: 1 = unoccluded
     // queues
-    uint32_t* q_trace;    // slot | WF_SHADOW_BIT
+    // The ray queue has one segment per ray kind so that a warp's 64-entry fetch is homogeneous:
+    // primary rays of neighbouring pixels stay together (coherent), sun-ward shadow rays share a
+    // direction, bounce rays are incoherent anyway. Entry = slot | WF_SHADOW_BIT.
+    uint32_t* q_trace;    // 3 segments of seg_cap entries
     uint32_t* q_far;
     uint32_t* q_near;
-    uint32_t* q_new;
     WaveCounters* cnt;
-    uint32_t n_slots;
+    uint32_t n_slots, seg_cap;
     int32_t tiles_x;
 };
 
@@ -86,11 +93,11 @@ __global__ void wf_init_kernel(WaveBuffers wb, RenderJob job)
     int lx, ly;
     const bool valid = slot_pixel(wb, job, slot, lx, ly) && (int)(slot % SAMPLE_LANES) < job.s_count;
     wb.sum[slot] = make_float4(0, 0, 0, 0);
-    wb.cursor[slot] = make_int2((int)(slot % SAMPLE_LANES), 0);
-    wb.q_new[slot] = valid ? slot : WF_INVALID;
+    wb.cursor[slot] = make_int2((int)(slot % SAMPLE_LANES), valid ? WF_NEED_SAMPLE : WF_FINISHED);
     if(slot == 0)
     {
-        wb.cnt->n_new = wb.n_slots; wb.cnt->n_trace = 0; wb.cnt->n_far = 0; wb.cnt->n_near = 0; wb.cnt->cur_trace = 0;
+        wb.cnt->n_new = 1; wb.cnt->n_seg[0] = 0; wb.cnt->n_seg[1] = 0; wb.cnt->n_seg[2] = 0;
+        wb.cnt->n_far = 0; wb.cnt->n_near = 0; wb.cnt->cur_trace = 0;
     }
 }
 
@@ -98,12 +105,14 @@ __global__ void wf_init_kernel(WaveBuffers wb, RenderJob job)
 __global__ void __launch_bounds__(256)
 wf_generate_kernel(Scene sc, RenderJob job, WaveBuffers wb)
 {
-    const uint32_t n = wb.cnt->n_new;
-    const uint32_t rounded = (n + 31u) & ~31u;
+    // Scans all slots in slot order (pixel tiles), so the primary rays of one 2x2-pixel block and one
+    // motion-blur subframe land next to each other in the primary segment.
+    if(wb.cnt->n_new == 0u) return;
+    const uint32_t rounded = (wb.n_slots + 31u) & ~31u;
     for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < rounded; i += gridDim.x * blockDim.x)
     {
-        const uint32_t slot = i < n ? wb.q_new[i] : WF_INVALID;
-        const bool ok = slot != WF_INVALID;
+        const uint32_t slot = i;
+        const bool ok = i < wb.n_slots && wb.cursor[i].y == WF_NEED_SAMPLE;
         if(ok)
         {
             int lx, ly;
@@ -126,7 +135,7 @@ wf_generate_kernel(Scene sc, RenderJob job, WaveBuffers wb)
             wb.nee[slot] = make_float4(0, 0, 0, 0);
             wb.cursor[slot] = make_int2(k, 0);
         }
-        wf_append(wb.q_trace, &wb.cnt->n_trace, ok, slot);
+        wf_append(wb.q_trace + WF_SEG_PRIMARY * (size_t)wb.seg_cap, &wb.cnt->n_seg[WF_SEG_PRIMARY], ok, slot);
     }
 }
 
@@ -138,7 +147,8 @@ __global__ void __launch_bounds__(WF_TRACE_THREADS, 6)
 wf_trace_kernel(Scene sc, RenderJob job, WaveBuffers wb)
 {
     const unsigned lane = threadIdx.x & 31u;
-    const uint32_t n_entries = wb.cnt->n_trace;
+    const uint32_t n_s0 = wb.cnt->n_seg[0], n_s1 = wb.cnt->n_seg[1], n_s2 = wb.cnt->n_seg[2];
+    const uint32_t n_entries = n_s0 + n_s1 + n_s2;
 
     // warp-uniform reserve of queue entries [res_base, res_base + res_n)
     uint32_t res_base = 0, res_n = 0;
@@ -225,7 +235,10 @@ wf_trace_kernel(Scene sc, RenderJob job, WaveBuffers wb)
             }
             if(entry_index != WF_INVALID)
             {
-                const uint32_t e = __ldg(wb.q_trace + entry_index);
+                // logical index over [bounce | primary | shadow] -> segment position
+                const uint32_t e = entry_index < n_s0 ? __ldg(wb.q_trace + entry_index) :
+                    entry_index - n_s0 < n_s1 ? __ldg(wb.q_trace + wb.seg_cap + (entry_index - n_s0)) :
+                    __ldg(wb.q_trace + 2 * (size_t)wb.seg_cap + (entry_index - n_s0 - n_s1));
                 if(e != WF_INVALID)
                 {
                     slot = e & ~WF_SHADOW_BIT;
@@ -373,7 +386,8 @@ __global__ void __launch_bounds__(WF_TRACE_THREADS, WF_CW_BLOCKS)
 wf_trace_cw_kernel(Scene sc, RenderJob job, WaveBuffers wb)
 {
     const unsigned lane = threadIdx.x & 31u;
-    const uint32_t n_entries = wb.cnt->n_trace;
+    const uint32_t n_s0 = wb.cnt->n_seg[0], n_s1 = wb.cnt->n_seg[1], n_s2 = wb.cnt->n_seg[2];
+    const uint32_t n_entries = n_s0 + n_s1 + n_s2;
     uint32_t res_base = 0, res_n = 0;
     bool exhausted = false;
     uint32_t far_base = 0, far_fill = 32, near_base = 0, near_fill = 32;
@@ -443,7 +457,10 @@ wf_trace_cw_kernel(Scene sc, RenderJob job, WaveBuffers wb)
             }
             if(entry_index != WF_INVALID)
             {
-                const uint32_t e = __ldg(wb.q_trace + entry_index);
+                // logical index over [bounce | primary | shadow] -> segment position
+                const uint32_t e = entry_index < n_s0 ? __ldg(wb.q_trace + entry_index) :
+                    entry_index - n_s0 < n_s1 ? __ldg(wb.q_trace + wb.seg_cap + (entry_index - n_s0)) :
+                    __ldg(wb.q_trace + 2 * (size_t)wb.seg_cap + (entry_index - n_s0 - n_s1));
                 if(e != WF_INVALID)
                 {
                     slot = e & ~WF_SHADOW_BIT;
@@ -650,9 +667,10 @@ wf_shade_kernel(Scene sc, RenderJob job, WaveBuffers wb)
                 float4 s = wb.sum[slot];
                 s.x += contribution.x; s.y += contribution.y; s.z += contribution.z;
                 wb.sum[slot] = s;
-                cursor.x += SAMPLE_LANES; cursor.y = 0;
-                wb.cursor[slot] = cursor;
+                cursor.x += SAMPLE_LANES;
                 push_new = cursor.x < job.s_count;
+                cursor.y = push_new ? WF_NEED_SAMPLE : WF_FINISHED;
+                wb.cursor[slot] = cursor;
             }
             else
             {
@@ -690,22 +708,21 @@ wf_shade_kernel(Scene sc, RenderJob job, WaveBuffers wb)
                 push_shadow = lit;
             }
         }
-        wf_append(wb.q_trace, &wb.cnt->n_trace, push_shadow, slot | WF_SHADOW_BIT);
-        wf_append(wb.q_trace, &wb.cnt->n_trace, push_ext, slot);
-        wf_append(wb.q_new, &wb.cnt->n_new, push_new, slot);
+        wf_append(wb.q_trace + WF_SEG_SHADOW * (size_t)wb.seg_cap, &wb.cnt->n_seg[WF_SEG_SHADOW], push_shadow, slot | WF_SHADOW_BIT);
+        wf_append(wb.q_trace + WF_SEG_BOUNCE * (size_t)wb.seg_cap, &wb.cnt->n_seg[WF_SEG_BOUNCE], push_ext, slot);
+        if(__any_sync(0xFFFFFFFFu, push_new) && (threadIdx.x & 31u) == 0u) atomicAdd(&wb.cnt->n_new, 1u);
     }
 }
 
 // ---- bookkeeping between phases ----------------------------------------------------------------------
-// phase 0: before generate+shade of the next round consume q_new / results: nothing to do
-// phase 1 (after trace): q_trace consumed -> reset it and the fetch cursor; q_new is refilled by shade
+// phase 1 (after trace): the ray queue is consumed -> reset it, the fetch cursor and the new-sample count (shade recounts)
 // phase 2 (after shade): result queues consumed -> reset; report whether any ray is left
 __global__ void wf_phase_kernel(WaveBuffers wb, int phase, uint32_t* host_visible_remaining)
 {
     if(threadIdx.x != 0 || blockIdx.x != 0) return;
     WaveCounters* c = wb.cnt;
-    if(phase == 1) { c->n_trace = 0; c->cur_trace = 0; c->n_new = 0; }
-    else if(phase == 2) { c->n_far = 0; c->n_near = 0; if(host_visible_remaining) *host_visible_remaining = c->n_trace + c->n_new; }
+    if(phase == 1) { c->n_seg[0] = 0; c->n_seg[1] = 0; c->n_seg[2] = 0; c->cur_trace = 0; c->n_new = 0; }
+    else if(phase == 2) { c->n_far = 0; c->n_near = 0; if(host_visible_remaining) *host_visible_remaining = c->n_seg[0] + c->n_seg[1] + c->n_seg[2] + c->n_new; }
 }
 
 // ---- finalize: fixed-order sum of the 8 slots of each pixel, mean, tonemap, pack ----------------------

@@ -189,8 +189,8 @@ int launch_wave(ptgpu_ctx* ctx, const Scene& sc, RenderJob job)
         o_sd = carve(16ull * n_slots), o_hit = carve(16ull * n_slots), o_prim = carve(4ull * n_slots),
         o_att = carve(16ull * n_slots), o_con = carve(16ull * n_slots), o_nee = carve(16ull * n_slots),
         o_sum = carve(16ull * n_slots), o_cur = carve(8ull * n_slots), o_vis = carve(4ull * n_slots),
-        o_qt = carve(4ull * (2ull * n_slots + q_pad)), o_qf = carve(4ull * (n_slots + q_pad)),
-        o_qn = carve(4ull * (n_slots + q_pad)), o_qw = carve(4ull * (n_slots + q_pad)), o_cnt = carve(sizeof(WaveCounters));
+        o_qt = carve(4ull * 3ull * (n_slots + 64)), o_qf = carve(4ull * (n_slots + q_pad)),
+        o_qn = carve(4ull * (n_slots + q_pad)), o_cnt = carve(sizeof(WaveCounters));
     if(ctx->wave_mem.reserve(off) != cudaSuccess) return -1;
     if(!ctx->wave_flag_host)
     {
@@ -204,8 +204,8 @@ int launch_wave(ptgpu_ctx* ctx, const Scene& sc, RenderJob job)
     wb.atten = (float4*)(m + o_att); wb.contrib = (float4*)(m + o_con); wb.nee = (float4*)(m + o_nee);
     wb.sum = (float4*)(m + o_sum); wb.cursor = (int2*)(m + o_cur); wb.visible = (uint32_t*)(m + o_vis);
     wb.q_trace = (uint32_t*)(m + o_qt); wb.q_far = (uint32_t*)(m + o_qf); wb.q_near = (uint32_t*)(m + o_qn);
-    wb.q_new = (uint32_t*)(m + o_qw); wb.cnt = (WaveCounters*)(m + o_cnt);
-    wb.n_slots = n_slots; wb.tiles_x = tiles_x;
+    wb.cnt = (WaveCounters*)(m + o_cnt);
+    wb.n_slots = n_slots; wb.seg_cap = n_slots + 64; wb.tiles_x = tiles_x;
     if(job.min_active < 1) job.min_active = 1;
     job.tri_threshold = ctx->tri_threshold; job.xform_threshold = ctx->xform_threshold;
     job.node_threshold = ctx->node_threshold; job.node_burst = ctx->node_burst;

@@ -15,9 +15,7 @@ def main():
     cfg = pkg.Config.testing()
     r = pkg.Renderer(cfg, 0)
     r.upload_static(**sio.load_static(sio.static_path()))
-    variants = []
-    for nt, nb, tt, xt in ((12, 4, 8, 4), (16, 4, 8, 4), (8, 4, 8, 4), (12, 8, 8, 4), (12, 2, 8, 4), (12, 4, 12, 4), (12, 4, 6, 2), (16, 8, 12, 6)):
-        variants.append(("cw n%d b%d t%d x%d" % (nt, nb, tt, xt), {"kernel": 2, "bvh": 1, "min_active": 8, "node_threshold": nt, "node_burst": nb, "tri_threshold": tt, "xform_threshold": xt}))
+    variants = [("wave default", {"kernel": 2})]
     try:
         if os.environ.get("PTGPU_NO_ORACLE"): raise RuntimeError()
         from oracle import refbind
