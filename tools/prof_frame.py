@@ -14,7 +14,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--frames", type=int, nargs="*", default=[520])
     ap.add_argument("--reps", type=int, default=2)
-    ap.add_argument("--kernel", type=int, default=0)
+    ap.add_argument("--kernel", type=int, default=2)
     ap.add_argument("--traversal", type=int, default=0)
     ap.add_argument("--spp", type=int, default=256)
     args = ap.parse_args()
