@@ -9,9 +9,10 @@
 //   * wf_shade<FAR> processes finished closest-hit queries sorted into two queues: FAR (miss or
 //     t >= 1e3: needs the sky ray-march, path_tracer.hh:513) and NEAR (skips it);
 //   * wf_generate starts the next sample of slots whose path ended (camera rays, :655-671).
-// A slot is (pixel, sample lane l): it traces samples k = l, l+8, ... of the job's sample set one
-// after another and keeps their running sum, exactly like a lane of the megakernel, so both give
-// identical images. All slots of the job live in the pool at once (state ~150 B per slot in HBM).
+// A slot is (pixel, sample lane l): it traces samples k = l, l+L, ... of the job's sample set one
+// after another and keeps their running sum. L (slots per pixel) is as large as the pool budget
+// allows — 256 at the shipped config, i.e. one sample per slot and five rounds per frame: with L = 8
+// (160 rounds) 23 % of all lane-iterations of wf_trace were idle in the tails of the launches.
 #pragma once
 #include "pt_kernels.cuh"
 #include "pt_wide.cuh"
@@ -58,7 +59,9 @@ struct WaveBuffers
     uint32_t* q_far;
     uint32_t* q_near;
     WaveCounters* cnt;
+    unsigned long long* stats;   // WF_STATS builds only
     uint32_t n_slots, seg_cap;
+    uint32_t lanes, lane_shift;  // slots per pixel (power of two): slot = pixel << lane_shift | lane
     int32_t tiles_x;
 };
 
@@ -66,7 +69,7 @@ constexpr int WF_TILE = 8;   // pixels per tile side in the slot order
 
 PT_D bool slot_pixel(const WaveBuffers& wb, const RenderJob& job, uint32_t slot, int& lx, int& ly)
 {
-    const uint32_t pi = slot / SAMPLE_LANES;
+    const uint32_t pi = slot >> wb.lane_shift;
     const uint32_t tile = pi / (WF_TILE * WF_TILE), in = pi % (WF_TILE * WF_TILE);
     lx = (int)(tile % wb.tiles_x) * WF_TILE + (int)(in % WF_TILE);
     ly = (int)(tile / wb.tiles_x) * WF_TILE + (int)(in / WF_TILE);
@@ -91,9 +94,9 @@ __global__ void wf_init_kernel(WaveBuffers wb, RenderJob job)
     const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
     if(slot >= wb.n_slots) return;
     int lx, ly;
-    const bool valid = slot_pixel(wb, job, slot, lx, ly) && (int)(slot % SAMPLE_LANES) < job.s_count;
+    const bool valid = slot_pixel(wb, job, slot, lx, ly) && (int)(slot & (wb.lanes - 1u)) < job.s_count;
     wb.sum[slot] = make_float4(0, 0, 0, 0);
-    wb.cursor[slot] = make_int2((int)(slot % SAMPLE_LANES), valid ? WF_NEED_SAMPLE : WF_FINISHED);
+    wb.cursor[slot] = make_int2((int)(slot & (wb.lanes - 1u)), valid ? WF_NEED_SAMPLE : WF_FINISHED);
     if(slot == 0)
     {
         wb.cnt->n_new = 1; wb.cnt->n_seg[0] = 0; wb.cnt->n_seg[1] = 0; wb.cnt->n_seg[2] = 0;
@@ -562,6 +565,22 @@ wf_trace_cw_kernel(Scene sc, RenderJob job, WaveBuffers wb)
         {
             advance();
             const bool w = wants_node();
+#ifdef WF_STATS
+            {
+                const int c_node = __popc(__ballot_sync(0xFFFFFFFFu, w));
+                const int c_idle = __popc(__ballot_sync(0xFFFFFFFFu, !active));
+                const int c_enter = __popc(__ballot_sync(0xFFFFFFFFu, wants_enter()));
+                const int c_pendfull = __popc(__ballot_sync(0xFFFFFFFFu, active && np >= CW_PEND));
+                const int c_exitwait = __popc(__ballot_sync(0xFFFFFFFFu, active && !w && !wants_enter() && np > 0 && np < CW_PEND));
+                if(lane == 0)
+                {
+                    atomicAdd(&wb.stats[0], 1ull); atomicAdd(&wb.stats[1], (unsigned long long)c_node);
+                    atomicAdd(&wb.stats[2], (unsigned long long)c_idle); atomicAdd(&wb.stats[3], (unsigned long long)c_enter);
+                    atomicAdd(&wb.stats[4], (unsigned long long)c_pendfull); atomicAdd(&wb.stats[5], (unsigned long long)c_exitwait);
+                    if(c_node >= job.node_threshold) atomicAdd(&wb.stats[6], 1ull);
+                }
+            }
+#endif
             if(__popc(__ballot_sync(0xFFFFFFFFu, w)) < job.node_threshold) break;
             if(w) node_step();
             progress = true;
@@ -573,6 +592,9 @@ wf_trace_cw_kernel(Scene sc, RenderJob job, WaveBuffers wb)
             #pragma unroll 1
             for(int b = 0; b < 3 && n >= job.tri_threshold; ++b)
             {
+#ifdef WF_STATS
+                if(lane == 0) { atomicAdd(&wb.stats[8], 1ull); atomicAdd(&wb.stats[9], (unsigned long long)n); }
+#endif
                 if(w) tri_step();
                 progress = true;
                 w = wants_tri();
@@ -585,6 +607,9 @@ wf_trace_cw_kernel(Scene sc, RenderJob job, WaveBuffers wb)
             const bool w = wants_enter();
             if(__popc(__ballot_sync(0xFFFFFFFFu, w)) >= job.xform_threshold)
             {
+#ifdef WF_STATS
+                { const int n_e = __popc(__ballot_sync(0xFFFFFFFFu, w)); if(lane == 0) { atomicAdd(&wb.stats[10], 1ull); atomicAdd(&wb.stats[11], (unsigned long long)n_e); } }
+#endif
                 if(w) enter_step();
                 progress = true;
             }
@@ -595,6 +620,9 @@ wf_trace_cw_kernel(Scene sc, RenderJob job, WaveBuffers wb)
             const int nn = __popc(__ballot_sync(0xFFFFFFFFu, wn));
             const int nt = __popc(__ballot_sync(0xFFFFFFFFu, wt));
             const int ne = __popc(__ballot_sync(0xFFFFFFFFu, we));
+#ifdef WF_STATS
+            if(lane == 0) { atomicAdd(&wb.stats[12], 1ull); atomicAdd(&wb.stats[13], (unsigned long long)nn); atomicAdd(&wb.stats[14], (unsigned long long)nt); atomicAdd(&wb.stats[15], (unsigned long long)ne); }
+#endif
             if(nn >= nt && nn >= ne) { if(wn) node_step(); }
             else if(nt >= ne) { if(wt) tri_step(); }
             else { if(we) enter_step(); }
@@ -667,7 +695,7 @@ wf_shade_kernel(Scene sc, RenderJob job, WaveBuffers wb)
                 float4 s = wb.sum[slot];
                 s.x += contribution.x; s.y += contribution.y; s.z += contribution.z;
                 wb.sum[slot] = s;
-                cursor.x += SAMPLE_LANES;
+                cursor.x += (int)wb.lanes;
                 push_new = cursor.x < job.s_count;
                 cursor.y = push_new ? WF_NEED_SAMPLE : WF_FINISHED;
                 wb.cursor[slot] = cursor;
@@ -725,27 +753,19 @@ __global__ void wf_phase_kernel(WaveBuffers wb, int phase, uint32_t* host_visibl
     else if(phase == 2) { c->n_far = 0; c->n_near = 0; if(host_visible_remaining) *host_visible_remaining = c->n_seg[0] + c->n_seg[1] + c->n_seg[2] + c->n_new; }
 }
 
-// ---- finalize: fixed-order sum of the 8 slots of each pixel, mean, tonemap, pack ----------------------
+// ---- finalize: fixed-order sum of the slots of each pixel, mean, tonemap, pack -------------------------
+// Lane sums are added in ascending lane order. With one sample per slot (lanes == samples per pixel,
+// the default when the pool fits) that is exactly the reference's order, j = 0 .. SPP-1 (main.cc:24-39).
 __global__ void wf_finalize_kernel(RenderJob job, WaveBuffers wb)
 {
     const uint32_t pi = blockIdx.x * blockDim.x + threadIdx.x;
-    if(pi * SAMPLE_LANES >= wb.n_slots) return;
+    if(((size_t)pi << wb.lane_shift) >= wb.n_slots) return;
     int lx, ly;
-    if(!slot_pixel(wb, job, pi * SAMPLE_LANES, lx, ly)) return;
-    v3 s[SAMPLE_LANES];
-    #pragma unroll
-    for(int l = 0; l < SAMPLE_LANES; ++l) { float4 f = wb.sum[pi * SAMPLE_LANES + l]; s[l] = mk3(f.x, f.y, f.z); }
-    // same tree as reduce_lanes (xor 1, 2, 4)
-    #pragma unroll
-    for(int m = 1; m < SAMPLE_LANES; m <<= 1)
-    {
-        v3 t[SAMPLE_LANES];
-        #pragma unroll
-        for(int l = 0; l < SAMPLE_LANES; ++l) t[l] = s[l] + s[l ^ m];
-        #pragma unroll
-        for(int l = 0; l < SAMPLE_LANES; ++l) s[l] = t[l];
-    }
-    store_pixel(job, lx, ly, s[0]);
+    if(!slot_pixel(wb, job, pi << wb.lane_shift, lx, ly)) return;
+    const float4* p = wb.sum + ((size_t)pi << wb.lane_shift);
+    v3 s = mk3(0, 0, 0);
+    for(uint32_t l = 0; l < wb.lanes; ++l) { const float4 f = p[l]; s += mk3(f.x, f.y, f.z); }
+    store_pixel(job, lx, ly, s);
 }
 
 } // namespace pt

@@ -61,6 +61,8 @@ struct ptgpu_ctx
     int kernel = 2;    // 0 megakernel, 1 simple tiles, 2 wavefront
     int min_active = -1; // -1: per-kernel default
     int bvh = 1;         // 0: 4-wide float BVH, 1: compressed 8-wide BVH
+    int max_lanes = 256;                       // wavefront: slots per pixel (power of two)
+    size_t pool_budget_bytes = 16ull << 30;    // wavefront: path-state pool budget
     int tri_threshold = 8, xform_threshold = 4, node_threshold = 12, node_burst = 2;
 
     // static scene, reference layout
@@ -181,7 +183,14 @@ int check_ready(ptgpu_ctx* ctx)
 int launch_wave(ptgpu_ctx* ctx, const Scene& sc, RenderJob job)
 {
     const int tiles_x = (job.w + WF_TILE - 1) / WF_TILE, tiles_y = (job.h + WF_TILE - 1) / WF_TILE;
-    const uint32_t n_slots = (uint32_t)tiles_x * tiles_y * WF_TILE * WF_TILE * SAMPLE_LANES;
+    // slots per pixel: the largest power of two <= the sample count that keeps the pool in budget
+    const size_t n_pix_padded = (size_t)tiles_x * tiles_y * WF_TILE * WF_TILE;
+    const size_t bytes_per_slot = 16 * 9 + 4 + 8 + 4 + 5 * 4;
+    uint32_t lanes = 1, lane_shift = 0;
+    while(lanes * 2 <= (uint32_t)job.s_count && lanes * 2 <= (uint32_t)ctx->max_lanes &&
+          n_pix_padded * (lanes * 2) * bytes_per_slot <= ctx->pool_budget_bytes && n_pix_padded * (lanes * 2) < 0x7FFF0000ull)
+    { lanes *= 2; lane_shift++; }
+    const uint32_t n_slots = (uint32_t)(n_pix_padded * lanes);
     const size_t q_pad = 32u * 1024u * 16u;
     size_t off = 0;
     auto carve = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~size_t(255); return o; };
@@ -190,7 +199,7 @@ int launch_wave(ptgpu_ctx* ctx, const Scene& sc, RenderJob job)
         o_att = carve(16ull * n_slots), o_con = carve(16ull * n_slots), o_nee = carve(16ull * n_slots),
         o_sum = carve(16ull * n_slots), o_cur = carve(8ull * n_slots), o_vis = carve(4ull * n_slots),
         o_qt = carve(4ull * 3ull * (n_slots + 64)), o_qf = carve(4ull * (n_slots + q_pad)),
-        o_qn = carve(4ull * (n_slots + q_pad)), o_cnt = carve(sizeof(WaveCounters));
+        o_qn = carve(4ull * (n_slots + q_pad)), o_cnt = carve(sizeof(WaveCounters)), o_stats = carve(16 * 8);
     if(ctx->wave_mem.reserve(off) != cudaSuccess) return -1;
     if(!ctx->wave_flag_host)
     {
@@ -205,17 +214,20 @@ int launch_wave(ptgpu_ctx* ctx, const Scene& sc, RenderJob job)
     wb.sum = (float4*)(m + o_sum); wb.cursor = (int2*)(m + o_cur); wb.visible = (uint32_t*)(m + o_vis);
     wb.q_trace = (uint32_t*)(m + o_qt); wb.q_far = (uint32_t*)(m + o_qf); wb.q_near = (uint32_t*)(m + o_qn);
     wb.cnt = (WaveCounters*)(m + o_cnt);
+    wb.stats = (unsigned long long*)(m + o_stats);
     wb.n_slots = n_slots; wb.seg_cap = n_slots + 64; wb.tiles_x = tiles_x;
+    wb.lanes = lanes; wb.lane_shift = lane_shift;
     if(job.min_active < 1) job.min_active = 1;
     job.tri_threshold = ctx->tri_threshold; job.xform_threshold = ctx->xform_threshold;
     job.node_threshold = ctx->node_threshold; job.node_burst = ctx->node_burst;
 
     cudaStream_t st = ctx->stream;
     int launches = 0;
+    cudaMemsetAsync(wb.stats, 0, 16 * 8, st);
     wf_init_kernel<<<(n_slots + 255) / 256, 256, 0, st>>>(wb, job); launches++;
     const int sms = ctx->sm_count;
     // worst case: every sample of a slot takes all bounces
-    const int samples_per_slot = (job.s_count + SAMPLE_LANES - 1) / SAMPLE_LANES;
+    const int samples_per_slot = (job.s_count + (int)lanes - 1) / (int)lanes;
     const int max_rounds = samples_per_slot * (sc.max_bounces + 1) + 2;
     const int check_every = 8;
     int rounds = 0;
@@ -237,7 +249,18 @@ int launch_wave(ptgpu_ctx* ctx, const Scene& sc, RenderJob job)
         if(*ctx->wave_flag_host == 0u || rounds >= max_rounds) break;
     }
     ctx->last_wave_rounds = rounds;
-    wf_finalize_kernel<<<(n_slots / SAMPLE_LANES + 255) / 256, 256, 0, st>>>(job, wb); launches++;
+#ifdef WF_STATS
+    {
+        unsigned long long h[16];
+        cudaMemcpyAsync(h, wb.stats, sizeof(h), cudaMemcpyDeviceToHost, st);
+        cudaStreamSynchronize(st);
+        fprintf(stderr, "WF_STATS node-iters %llu (executed %llu): lanes node %.2f idle %.2f enter-wait %.2f pend-full %.2f tri-wait %.2f | tri steps %llu lanes %.2f | enter steps %llu lanes %.2f | forced %llu (n %.2f t %.2f e %.2f)\n",
+                h[0], h[6], (double)h[1] / h[0], (double)h[2] / h[0], (double)h[3] / h[0], (double)h[4] / h[0], (double)h[5] / h[0],
+                h[8], h[8] ? (double)h[9] / h[8] : 0.0, h[10], h[10] ? (double)h[11] / h[10] : 0.0,
+                h[12], h[12] ? (double)h[13] / h[12] : 0.0, h[12] ? (double)h[14] / h[12] : 0.0, h[12] ? (double)h[15] / h[12] : 0.0);
+    }
+#endif
+    wf_finalize_kernel<<<(unsigned)((n_pix_padded + 255) / 256), 256, 0, st>>>(job, wb); launches++;
     return launches;
 }
 
@@ -795,6 +818,8 @@ int ptgpu_set_option(ptgpu_ctx* ctx, const char* key, int64_t value)
     if(!strcmp(key, "xform_threshold")) { if(value < 1 || value > 32) return fail(ctx, "xform_threshold must be 1..32"); ctx->xform_threshold = (int)value; return 0; }
     if(!strcmp(key, "node_threshold")) { if(value < 1 || value > 32) return fail(ctx, "node_threshold must be 1..32"); ctx->node_threshold = (int)value; return 0; }
     if(!strcmp(key, "node_burst")) { if(value < 1 || value > 64) return fail(ctx, "node_burst must be 1..64"); ctx->node_burst = (int)value; return 0; }
+    if(!strcmp(key, "lanes")) { if(value < 1 || value > 4096 || (value & (value - 1))) return fail(ctx, "lanes must be a power of two in 1..4096"); ctx->max_lanes = (int)value; return 0; }
+    if(!strcmp(key, "pool_budget_mb")) { if(value < 1) return fail(ctx, "pool_budget_mb must be positive"); ctx->pool_budget_bytes = (size_t)value << 20; return 0; }
     if(!strcmp(key, "min_active")) { if(value < -1 || value > 32) return fail(ctx, "min_active must be -1..32"); ctx->min_active = (int)value; return 0; }
     return fail(ctx, "unknown option '%s'", key);
 }
