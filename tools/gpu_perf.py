@@ -15,8 +15,7 @@ def main():
     cfg = pkg.Config.testing()
     r = pkg.Renderer(cfg, 0)
     r.upload_static(**sio.load_static(sio.static_path()))
-    variants = [("lanes 8", {"kernel": 2, "lanes": 8}), ("lanes 32", {"kernel": 2, "lanes": 32}), ("lanes 256", {"kernel": 2, "lanes": 256}),
-                ("lanes 256 r4", {"kernel": 2, "lanes": 256, "min_active": 4})]
+    variants = [("default", {"kernel": 2})]
     try:
         if os.environ.get("PTGPU_NO_ORACLE"): raise RuntimeError()
         from oracle import refbind
