@@ -203,7 +203,12 @@ int ptgpu_last_render_ms(ptgpu_ctx* ctx, float* ms, int32_t* launches);
  *              (stackless, ray_query.hh:184-223) — the counting / cross-check mode
  * "counters":  1 = count per-path events (rays, node visits, triangle tests, ...) on the
  *              reference link tables; only with traversal = 1
- * "kernel":    0 = persistent megakernel (default), 1 = simple one-thread-per-path kernel */
+ * "kernel":    2 = wavefront (default), 0 = persistent megakernel, 1 = one-thread-per-path tile kernel
+ * "bvh":       1 = compressed 8-wide BVH (default, wavefront only), 0 = 4-wide float BVH
+ * "lanes", "pool_budget_mb": path slots per pixel of the wavefront pool (power of two) and its budget
+ * "min_active", "node_threshold", "node_burst", "tri_threshold", "xform_threshold": warp scheduling
+ *              of the traversal kernels (see csrc/pt_wave.cuh); results do not depend on them
+ * "validate":  1 = cross-check every traversal query (debug, slow), see ptgpu_get_stat */
 int ptgpu_set_option(ptgpu_ctx* ctx, const char* key, int64_t value);
 
 enum {
@@ -217,6 +222,12 @@ int ptgpu_read_counters(ptgpu_ctx* ctx, uint64_t out[PTGPU_CNT_COUNT]);
 /* Sizes of the device-side scene, for reporting: out = {static bytes, per-frame bytes,
  * wide-BVH nodes, triangles, static instances}. */
 int ptgpu_scene_stats(ptgpu_ctx* ctx, uint64_t out[8]);
+
+/* Facts about the most recent wavefront render: "wave_rounds", "wave_lanes" (path slots per pixel),
+ * "pool_bytes" (path-state pool), "validate_mismatches" (with option "validate" = 1 every ray of
+ * every round is re-traced with the plain single-ray traversal and compared with what the scheduled
+ * traversal kernel stored; the number of disagreeing queries). */
+int ptgpu_get_stat(ptgpu_ctx* ctx, const char* key, uint64_t* out);
 
 /* Host-only, needs no GPU: runs the BVH flattening that ptgpu_upload_static performs on the
  * reference arrays (bvh.cc:43-229 output) and checks the result structurally (every triangle

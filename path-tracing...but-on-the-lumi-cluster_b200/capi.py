@@ -15,7 +15,7 @@ SYMBOLS = [
     "ptgpu_render_rect", "ptgpu_trace_samples", "ptgpu_tonemap", "ptgpu_trace_closest",
     "ptgpu_pcg4d", "ptgpu_render_async", "ptgpu_fetch_bgra", "ptgpu_fetch_bmp", "ptgpu_sync",
     "ptgpu_last_render_ms", "ptgpu_set_option", "ptgpu_read_counters", "ptgpu_scene_stats",
-    "ptgpu_host_flatten_check",
+    "ptgpu_host_flatten_check", "ptgpu_get_stat",
 ]
 
 
@@ -94,6 +94,7 @@ def load_library():
     L.ptgpu_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
     L.ptgpu_read_counters.argtypes = [vp, C.POINTER(C.c_uint64)]
     L.ptgpu_scene_stats.argtypes = [vp, C.POINTER(C.c_uint64)]
+    L.ptgpu_get_stat.argtypes = [vp, C.c_char_p, C.POINTER(C.c_uint64)]
     L.ptgpu_host_flatten_check.argtypes = [vp, sz, vp, sz, vp, sz, vp, sz, vp, sz, C.POINTER(C.c_uint64), C.c_char_p, sz]
     for name in SYMBOLS:
         if name not in ("ptgpu_default_config", "ptgpu_destroy", "ptgpu_last_error", "ptgpu_bmp_size"):

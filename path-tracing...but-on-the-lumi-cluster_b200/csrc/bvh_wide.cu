@@ -842,6 +842,7 @@ uint64_t verify_wide_scene(const WideScene& ws, size_t n_static, std::string& er
 
     // compressed 8-wide layout: decode every node the way the kernel does and repeat the checks
     auto walk_cw = [&](uint32_t root, bool tlas, std::vector<uint32_t>& payload_seen, uint32_t payload_lo, uint32_t payload_hi) {
+        // `box` = intersection of the slot boxes of all ancestors: what a ray must hit to get here
         struct Todo { uint32_t node; Box box; bool has_box; };
         std::vector<Todo> todo{{root, Box(), false}};
         while(!todo.empty())
@@ -872,7 +873,9 @@ uint64_t verify_wide_scene(const WideScene& ws, size_t n_static, std::string& er
                 if(inner)
                 {
                     if((meta & 0x1F) != 24u + (uint32_t)s) fail("inner meta does not encode its slot");
-                    todo.push_back({child_base + inner_rank, cb, true});
+                    Box nb = cb;
+                    if(t.has_box) for(int a = 0; a < 3; ++a) { nb.lo[a] = std::max(nb.lo[a], t.box.lo[a]); nb.hi[a] = std::min(nb.hi[a], t.box.hi[a]); }
+                    todo.push_back({child_base + inner_rank, nb, true});
                     inner_rank++;
                     continue;
                 }
@@ -900,6 +903,9 @@ uint64_t verify_wide_scene(const WideScene& ws, size_t n_static, std::string& er
                         {
                             const float pp[3] = {v[c].x, v[c].y, v[c].z};
                             for(int a = 0; a < 3; ++a) if(pp[a] < cb.lo[a] || pp[a] > cb.hi[a]) fail("triangle vertex outside its quantised leaf box");
+                            if(t.has_box)
+                                for(int a = 0; a < 3; ++a) if(pp[a] < t.box.lo[a] || pp[a] > t.box.hi[a])
+                                    fail("triangle " + std::to_string(idx) + " vertex outside an ancestor's slot box (node " + std::to_string(t.node) + ")");
                         }
                     }
                 }

@@ -19,6 +19,26 @@ namespace pt {
 
 #define CW_MARK_X 0xFFFFFFFFu
 
+// Traversal stack storage. LocalStack: a per-thread array (local memory). HybridStack: the first
+// CW_SM_STACK entries in shared memory laid out [entry][thread] (bank = thread, conflict-free for any
+// mix of depths), the rest in local memory. ncu on the all-local version: the loads of the stack top
+// and of the pending-triangle list were the top three stall sites of wf_trace_cw (25 % of samples).
+constexpr int CW_SM_STACK = 14;
+struct LocalStack
+{
+    uint2* p;
+    PT_D void set(int i, uint2 v) { p[i] = v; }
+    PT_D uint2 get(int i) const { return p[i]; }
+};
+struct HybridStack
+{
+    uint2* sm;      // &shared[0][thread]
+    uint2* lo;      // overflow (local memory)
+    int stride;     // threads per block
+    PT_D void set(int i, uint2 v) { if(i < CW_SM_STACK) sm[i * stride] = v; else lo[i - CW_SM_STACK] = v; }
+    PT_D uint2 get(int i) const { return i < CW_SM_STACK ? sm[i * stride] : lo[i - CW_SM_STACK]; }
+};
+
 struct CwState
 {
     v3 ro, rd;          // world-space ray
@@ -73,6 +93,11 @@ PT_D void cw_intersect_node(const float4* __restrict__ nodes, uint32_t node_inde
     const float ax = sx * st.idir.x, ay = sy * st.idir.y, az = sz * st.idir.z;
     const float ox = (n0.x - st.o.x) * st.idir.x, oy = (n0.y - st.o.y) * st.idir.y, oz = (n0.z - st.o.z) * st.idir.z;
     const bool nx = st.sign_bits & 1u, ny = st.sign_bits & 2u, nz = st.sign_bits & 4u;
+    // Boxes are culled against a slightly longer ray than the triangles: the box arithmetic rounds, so
+    // with the exact tmax a node holding a hit a few ulp closer than the current one could be skipped or
+    // not depending on the order in which the two were found (coincident leaf cards in the tree
+    // meshes). With the slack the closest hit is found in any order: results stay deterministic.
+    const float tmax_box = fmaf(st.tmax, 1.0e-5f, st.tmax);
     uint32_t hitmask = 0;
     #pragma unroll
     for(int half = 0; half < 2; ++half)
@@ -95,7 +120,7 @@ PT_D void cw_intersect_node(const float4* __restrict__ nodes, uint32_t node_inde
             const float t0y = fmaf(u8f(y_near, j), ay, oy), t1y = fmaf(u8f(y_far, j), ay, oy);
             const float t0z = fmaf(u8f(z_near, j), az, oz), t1z = fmaf(u8f(z_far, j), az, oz);
             const float cmin = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, st.tmin));
-            const float cmax = fminf(fminf(t1x, t1y), fminf(t1z, st.tmax));
+            const float cmax = fminf(fminf(t1x, t1y), fminf(t1z, tmax_box));
             if(cmin <= cmax)
                 hitmask |= ((child_bits4 >> (8 * j)) & 0xFFu) << ((bit_index4 >> (8 * j)) & 0xFFu);
         }
@@ -108,7 +133,8 @@ PT_D void cw_intersect_node(const float4* __restrict__ nodes, uint32_t node_inde
 
 // Query start: the subframe's dynamic instances (world-box test) go on the stack as one instance
 // group, then the static TLAS root is the first node group.
-PT_D void cw_begin(const Scene& sc, CwState& st, uint2* stack, uint32_t subframe, v3 ro, v3 rd,
+template<class Stack>
+PT_D void cw_begin(const Scene& sc, CwState& st, Stack& stack, uint32_t subframe, v3 ro, v3 rd,
                    float tmin, float tmax, bool any)
 {
     st.ro = ro; st.rd = rd; st.tmin = tmin; st.tmax = tmax; st.any = any; st.subframe = subframe;
@@ -124,7 +150,7 @@ PT_D void cw_begin(const Scene& sc, CwState& st, uint2* stack, uint32_t subframe
         const WideInstance* wi = sc.winst + id;
         if(box_hit(__ldg(&wi->lo), __ldg(&wi->hi), ro, st.idir, tmin, tmax)) mask |= 1u << k;
     }
-    if(mask) stack[st.sp++] = make_uint2(0x80000000u, mask);
+    if(mask) stack.set(st.sp++, make_uint2(0x80000000u, mask));
     st.ngroup = make_uint2(sc.cw_tlas_root, 0x80000000u);
     st.tgroup = make_uint2(0u, 0u);
 }
@@ -141,7 +167,8 @@ PT_D uint32_t cw_decode_instance(const Scene& sc, const CwState& st, uint32_t ba
 }
 
 // ray_query_enter_blas (ray_query.hh:153-182) on the compressed layout
-PT_D void cw_enter_instance(const Scene& sc, CwState& st, uint2* stack, uint32_t id)
+template<class Stack>
+PT_D void cw_enter_instance(const Scene& sc, CwState& st, Stack& stack, uint32_t id)
 {
     st.cur_inst = id;
     const WideInstance* wi = sc.winst + id;
@@ -156,7 +183,7 @@ PT_D void cw_enter_instance(const Scene& sc, CwState& st, uint2* stack, uint32_t
     cw_set_space(st, o, d);
     tri_preprocess(d, st.axis, st.S);
     st.in_blas = true;
-    stack[st.sp++] = make_uint2(CW_MARK_X, 0u);
+    stack.set(st.sp++, make_uint2(CW_MARK_X, 0u));
     st.ngroup = make_uint2(root, 0x80000000u);
     st.tgroup = make_uint2(0u, 0u);
 }
@@ -185,7 +212,8 @@ PT_D void cw_test_triangle(const Scene& sc, CwState& st, uint32_t tri)
 }
 
 // node phase: take the next child of the node group (highest bit = nearest in octant order), test it
-PT_D void cw_node_phase(const Scene& sc, CwState& st, uint2* stack)
+template<class Stack>
+PT_D void cw_node_phase(const Scene& sc, CwState& st, Stack& stack)
 {
     if(st.ngroup.y > 0x00FFFFFFu)
     {
@@ -193,7 +221,7 @@ PT_D void cw_node_phase(const Scene& sc, CwState& st, uint2* stack)
         const uint32_t child_bit = 31u - (uint32_t)__clz(hits_imask);
         const uint32_t base = st.ngroup.x;
         st.ngroup.y &= ~(1u << child_bit);
-        if(st.ngroup.y > 0x00FFFFFFu) stack[st.sp++] = st.ngroup;
+        if(st.ngroup.y > 0x00FFFFFFu) stack.set(st.sp++, st.ngroup);
         const uint32_t slot = (child_bit - 24u) ^ (st.oct_inv4 & 0xFFu);
         const uint32_t rel = (uint32_t)__popc(hits_imask & ~(0xFFFFFFFFu << slot));
         cw_intersect_node(sc.cwnodes, base + rel, st, st.ngroup, st.tgroup);
@@ -206,22 +234,24 @@ PT_D void cw_node_phase(const Scene& sc, CwState& st, uint2* stack)
 }
 
 // instance phase (TLAS context): enter one instance of the leaf group, park everything else
-PT_D void cw_instance_phase(const Scene& sc, CwState& st, uint2* stack)
+template<class Stack>
+PT_D void cw_instance_phase(const Scene& sc, CwState& st, Stack& stack)
 {
     const uint32_t bit = 31u - (uint32_t)__clz(st.tgroup.y);
     st.tgroup.y &= ~(1u << bit);
-    if(st.ngroup.y > 0x00FFFFFFu) stack[st.sp++] = st.ngroup;
-    if(st.tgroup.y) stack[st.sp++] = st.tgroup;
+    if(st.ngroup.y > 0x00FFFFFFu) stack.set(st.sp++, st.ngroup);
+    if(st.tgroup.y) stack.set(st.sp++, st.tgroup);
     cw_enter_instance(sc, st, stack, cw_decode_instance(sc, st, st.tgroup.x, bit));
 }
 
 // pop phase; returns false when the query is complete
-PT_D bool cw_pop_phase(CwState& st, uint2* stack)
+template<class Stack>
+PT_D bool cw_pop_phase(CwState& st, Stack& stack)
 {
     if(st.ngroup.y <= 0x00FFFFFFu)
     {
         if(st.sp == 0) return false;
-        const uint2 e = stack[--st.sp];
+        const uint2 e = stack.get(--st.sp);
         if(e.y == 0u)
         {   // exit marker: BLAS finished, back to world space
             st.in_blas = false;
@@ -236,7 +266,8 @@ PT_D bool cw_pop_phase(CwState& st, uint2* stack)
 template<bool ANY>
 PT_D bool trace_cw(const Scene& sc, uint32_t subframe, v3 origin, v3 dir, float tmin, float tmax, Hit& hit)
 {
-    uint2 stack[CW_STACK];
+    uint2 stack_mem[CW_STACK];
+    LocalStack stack{stack_mem};
     CwState st;
     cw_begin(sc, st, stack, subframe, origin, dir, tmin, tmax, ANY);
     for(;;)

@@ -32,27 +32,42 @@ PT_D void tri_preprocess(v3 dir, int& axis, v3& S)
 
 // ray_triangle_intersection (math.hh:358-401). Returns the reference's hit predicate; t,u,v are
 // the components of *uvt.
+// Every product and sum is written with an explicit-rounding intrinsic so that nvcc cannot contract
+// them differently at different inlining sites: with free contraction a degenerate triangle
+// (three identical vertices: the dragon mesh has some) gave cross products that were rounding
+// residues instead of exact zeros, with a sign pattern that depended on which copy of this function
+// ran — a spurious hit in one kernel and none in another, and run-to-run differences in the
+// scheduled traversal kernel, which inlines the test at two sites. Written this way det is exactly
+// zero for such triangles (rejected, as in the reference's strict-math semantics) and every copy
+// of the function returns identical bits.
 PT_D bool tri_intersect(v3 origin, int axis, v3 S, v3 p0, v3 p1, v3 p2,
                         float& u, float& v, float& t, bool& back_face)
 {
-    v3 A = p0 - origin, B = p1 - origin, C = p2 - origin;
-    v3 x = mk3(A.x, B.x, C.x), y = mk3(A.y, B.y, C.y), z = mk3(A.z, B.z, C.z);
-    if(axis == 0) { v3 tmp = x; x = z; z = tmp; }
-    else if(axis == 1) { v3 tmp = y; y = z; z = tmp; }
-    x = x - S.x * z;
-    y = y - S.y * z;
-    v3 uvw = cross(y, x);
-    float det = uvw.x + uvw.y + uvw.z;
-    float inv = 1.0f / det;
-    u = uvw.x * inv;
-    v = uvw.y * inv;
-    t = dot(uvw, S.z * z) * inv;
-    back_face = det < 0.0f;
-    if(S.z < 0.0f) back_face = !back_face;
-    if(axis != 2) back_face = !back_face;
+    const float Ax0 = __fsub_rn(p0.x, origin.x), Ay0 = __fsub_rn(p0.y, origin.y), Az0 = __fsub_rn(p0.z, origin.z);
+    const float Bx0 = __fsub_rn(p1.x, origin.x), By0 = __fsub_rn(p1.y, origin.y), Bz0 = __fsub_rn(p1.z, origin.z);
+    const float Cx0 = __fsub_rn(p2.x, origin.x), Cy0 = __fsub_rn(p2.y, origin.y), Cz0 = __fsub_rn(p2.z, origin.z);
+    // math.hh:376-385: axis 0 swaps x and z, axis 1 swaps y and z
+    const bool a0 = axis == 0, a1 = axis == 1;
+    const float Az = a0 ? Ax0 : a1 ? Ay0 : Az0, Bz = a0 ? Bx0 : a1 ? By0 : Bz0, Cz = a0 ? Cx0 : a1 ? Cy0 : Cz0;
+    const float Ax = a0 ? Az0 : Ax0, Bx = a0 ? Bz0 : Bx0, Cx = a0 ? Cz0 : Cx0;
+    const float Ay = a1 ? Az0 : Ay0, By = a1 ? Bz0 : By0, Cy = a1 ? Cz0 : Cy0;
+    // x -= S.x * z; y -= S.y * z (math.hh:387-388)
+    const float xa = __fmaf_rn(-S.x, Az, Ax), xb = __fmaf_rn(-S.x, Bz, Bx), xc = __fmaf_rn(-S.x, Cz, Cx);
+    const float ya = __fmaf_rn(-S.y, Az, Ay), yb = __fmaf_rn(-S.y, Bz, By), yc = __fmaf_rn(-S.y, Cz, Cy);
+    // uvw = cross(y, x) (math.hh:390): both products rounded, then subtracted
+    const float U = __fsub_rn(__fmul_rn(yb, xc), __fmul_rn(yc, xb));
+    const float V = __fsub_rn(__fmul_rn(yc, xa), __fmul_rn(ya, xc));
+    const float W = __fsub_rn(__fmul_rn(ya, xb), __fmul_rn(yb, xa));
+    const float det = __fadd_rn(__fadd_rn(U, V), W);
+    const float inv = __fdiv_rn(1.0f, det);
+    u = __fmul_rn(U, inv);
+    v = __fmul_rn(V, inv);
+    // dot(uvw, S.z * z) * (1 / det) (math.hh:392)
+    const float dz = __fmaf_rn(W, __fmul_rn(S.z, Cz), __fmaf_rn(V, __fmul_rn(S.z, Bz), __fmul_rn(U, __fmul_rn(S.z, Az))));
+    t = __fmul_rn(dz, inv);
+    back_face = (det < 0.0f) != ((S.z < 0.0f) != (axis != 2)); // math.hh:393-395
     return det != 0.0f && t >= 0.0f &&
-        ((uvw.x >= 0.0f && uvw.y >= 0.0f && uvw.z >= 0.0f) ||
-         (uvw.x <= 0.0f && uvw.y <= 0.0f && uvw.z <= 0.0f));
+        ((U >= 0.0f && V >= 0.0f && W >= 0.0f) || (U <= 0.0f && V <= 0.0f && W <= 0.0f));
 }
 
 PT_D v3 safe_inv_dir(v3 d)

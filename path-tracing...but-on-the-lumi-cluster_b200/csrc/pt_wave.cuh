@@ -398,8 +398,11 @@ wf_trace_cw_kernel(Scene sc, RenderJob job, WaveBuffers wb)
     bool active = false;
     int done_class = 0;
     uint32_t slot = 0;
-    uint2 stack[CW_STACK];
-    uint2 pend[CW_PEND];
+    __shared__ uint2 s_stack[CW_SM_STACK][WF_TRACE_THREADS];
+    __shared__ uint2 s_pend[CW_PEND][WF_TRACE_THREADS];
+    uint2 stack_overflow[CW_STACK - CW_SM_STACK];
+    HybridStack stack{&s_stack[0][threadIdx.x], stack_overflow, WF_TRACE_THREADS};
+    uint2* pend = &s_pend[0][threadIdx.x];   // entry i at pend[i * WF_TRACE_THREADS]
     int np = 0;
     CwState st;
     st.ngroup = make_uint2(0u, 0u); st.tgroup = make_uint2(0u, 0u); st.sp = 0; st.in_blas = false; st.any = false;
@@ -505,13 +508,13 @@ wf_trace_cw_kernel(Scene sc, RenderJob job, WaveBuffers wb)
                 }
                 else
                 {
-                    const uint2 e = stack[st.sp - 1];
+                    const uint2 e = stack.get(st.sp - 1);
                     if(e.y == 0u)
                     {   // exit marker: leave the instance once its pending triangles are done
                         if(np == 0)
                         {
                             st.sp -= 3;
-                            const uint2 a = stack[st.sp], b = stack[st.sp + 1];
+                            const uint2 a = stack.get(st.sp), b = stack.get(st.sp + 1);
                             st.o = st.ro;
                             st.idir = mk3(__uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(b.x));
                             st.oct_inv4 = (b.y & 0xFFu) * 0x01010101u;
@@ -534,16 +537,16 @@ wf_trace_cw_kernel(Scene sc, RenderJob job, WaveBuffers wb)
             cw_node_phase(sc, st, stack);
             if(st.tgroup.y != 0u)
             {
-                if(st.in_blas) { pend[np++] = st.tgroup; st.tgroup.y = 0u; }              // triangles wait for the TRI block
-                else if(st.ngroup.y > 0x00FFFFFFu) { stack[st.sp++] = st.tgroup; st.tgroup.y = 0u; } // instances wait below the TLAS nodes
+                if(st.in_blas) { pend[(np++) * WF_TRACE_THREADS] = st.tgroup; st.tgroup.y = 0u; }              // triangles wait for the TRI block
+                else if(st.ngroup.y > 0x00FFFFFFu) { stack.set(st.sp++, st.tgroup); st.tgroup.y = 0u; } // instances wait below the TLAS nodes
             }
         };
         auto tri_step = [&]() {
             // one triangle of the newest pending leaf group
-            uint2 g = pend[np - 1];
+            uint2 g = pend[(np - 1) * WF_TRACE_THREADS];
             const uint32_t bit = 31u - (uint32_t)__clz(g.y);
             g.y &= ~(1u << bit);
-            if(g.y) pend[np - 1] = g; else np--;
+            if(g.y) pend[(np - 1) * WF_TRACE_THREADS] = g; else np--;
             cw_test_triangle(sc, st, g.x + bit);
             if(st.any && st.hit.t >= 0.0f) np = 0; // any hit ends a shadow query (sp and groups are cleared)
         };
@@ -552,9 +555,9 @@ wf_trace_cw_kernel(Scene sc, RenderJob job, WaveBuffers wb)
             // parked under the exit marker, which makes leaving the instance a few loads
             const uint32_t bit = 31u - (uint32_t)__clz(st.tgroup.y);
             st.tgroup.y &= ~(1u << bit);
-            if(st.tgroup.y) stack[st.sp++] = st.tgroup;
-            stack[st.sp++] = make_uint2(__float_as_uint(st.idir.x), __float_as_uint(st.idir.y));
-            stack[st.sp++] = make_uint2(__float_as_uint(st.idir.z), (st.oct_inv4 & 0xFFu) | (st.sign_bits << 8));
+            if(st.tgroup.y) stack.set(st.sp++, st.tgroup);
+            stack.set(st.sp++, make_uint2(__float_as_uint(st.idir.x), __float_as_uint(st.idir.y)));
+            stack.set(st.sp++, make_uint2(__float_as_uint(st.idir.z), (st.oct_inv4 & 0xFFu) | (st.sign_bits << 8)));
             cw_enter_instance(sc, st, stack, cw_decode_instance(sc, st, st.tgroup.x, bit));
         };
 
@@ -630,6 +633,47 @@ wf_trace_cw_kernel(Scene sc, RenderJob job, WaveBuffers wb)
     }
     if(near_fill < 32u && near_fill + lane < 32u) wb.q_near[near_base + near_fill + lane] = WF_INVALID;
     if(far_fill < 32u && far_fill + lane < 32u) wb.q_far[far_base + far_fill + lane] = WF_INVALID;
+}
+
+// ---- debug: re-trace every queue entry with the plain single-ray traversal and compare ---------------
+// (ptgpu_set_option "validate" = 1; counts and prints mismatches of the scheduled kernel)
+__global__ void wf_validate_kernel(Scene sc, RenderJob job, WaveBuffers wb, unsigned long long* mismatch)
+{
+    const uint32_t n_s0 = wb.cnt->n_seg[0], n_s1 = wb.cnt->n_seg[1], n_s2 = wb.cnt->n_seg[2];
+    const uint32_t n = n_s0 + n_s1 + n_s2;
+    for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    {
+        const uint32_t e = i < n_s0 ? wb.q_trace[i] : i - n_s0 < n_s1 ? wb.q_trace[wb.seg_cap + (i - n_s0)] : wb.q_trace[2 * (size_t)wb.seg_cap + (i - n_s0 - n_s1)];
+        if(e == WF_INVALID) continue;
+        const uint32_t slot = e & ~WF_SHADOW_BIT;
+        const bool shadow = (e & WF_SHADOW_BIT) != 0u;
+        const float4 fo = wb.ray_o[slot];
+        const float4 fd = shadow ? wb.shadow_d[slot] : wb.ray_d[slot];
+        const int sample = job.s_begin + wb.cursor[slot].x * job.s_stride;
+        const uint32_t subframe = sample < 0 ? 0u : (uint32_t)sample / (uint32_t)sc.samples_per_subframe;
+        Hit h;
+        if(shadow)
+        {
+            trace_cw<true>(sc, subframe, mk3(fo.x, fo.y, fo.z), mk3(fd.x, fd.y, fd.z), fo.w, PT_MAX_RAY_DIST, h);
+            const uint32_t vis = h.t < 0.0f ? 1u : 0u;
+            if(vis != wb.visible[slot])
+            {
+                if(atomicAdd(mismatch, 1ull) < 8ull) printf("validate: shadow slot %u vis %u vs %u\n", slot, wb.visible[slot], vis);
+            }
+        }
+        else
+        {
+            trace_cw<false>(sc, subframe, mk3(fo.x, fo.y, fo.z), mk3(fd.x, fd.y, fd.z), fo.w, PT_MAX_RAY_DIST, h);
+            const float4 fh = wb.hit[slot];
+            const uint32_t hp = wb.hit_prim[slot];
+            if(fh.x != h.t || (h.t >= 0.0f && (__float_as_uint(fh.w) != h.inst || (hp & 0x7FFFFFFFu) != h.prim)))
+            {
+                if(atomicAdd(mismatch, 1ull) < 8ull)
+                    printf("validate: slot %u sub %u o %.7g %.7g %.7g d %.7g %.7g %.7g tmin %g: kernel t %.9g inst %u prim %u | plain t %.9g inst %u prim %u\n",
+                           slot, subframe, fo.x, fo.y, fo.z, fd.x, fd.y, fd.z, fo.w, fh.x, __float_as_uint(fh.w), hp & 0x7FFFFFFFu, h.t, h.inst, h.prim);
+            }
+        }
+    }
 }
 
 // ---- shade: a closest-hit query finished (trace_ray tail + bounce loop body) -----------------------

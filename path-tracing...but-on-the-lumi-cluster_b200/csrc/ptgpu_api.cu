@@ -61,6 +61,7 @@ struct ptgpu_ctx
     int kernel = 2;    // 0 megakernel, 1 simple tiles, 2 wavefront
     int min_active = -1; // -1: per-kernel default
     int bvh = 1;         // 0: 4-wide float BVH, 1: compressed 8-wide BVH
+    int validate = 0;                          // debug: re-trace every ray with the plain traversal and compare
     int max_lanes = 256;                       // wavefront: slots per pixel (power of two)
     size_t pool_budget_bytes = 16ull << 30;    // wavefront: path-state pool budget
     int tri_threshold = 8, xform_threshold = 4, node_threshold = 12, node_burst = 2;
@@ -105,6 +106,9 @@ struct ptgpu_ctx
     DevBuf<uint32_t> wave_flag;
     uint32_t* wave_flag_host = nullptr;
     int last_wave_rounds = 0;
+    uint32_t last_wave_lanes = 0;
+    size_t last_pool_bytes = 0;
+    unsigned long long last_validate_mismatches = 0;
     uint32_t bmp_pitch = 0;
     bool bmp_header_done = false;
     bool render_pending = false;
@@ -238,6 +242,7 @@ int launch_wave(ptgpu_ctx* ctx, const Scene& sc, RenderJob job)
             wf_generate_kernel<<<sms * 4, 256, 0, st>>>(sc, job, wb);
             if(ctx->bvh == 1) wf_trace_cw_kernel<<<sms * WF_CW_BLOCKS, WF_TRACE_THREADS, 0, st>>>(sc, job, wb);
             else wf_trace_kernel<<<sms * 6, WF_TRACE_THREADS, 0, st>>>(sc, job, wb);
+            if(ctx->validate && ctx->bvh == 1) wf_validate_kernel<<<sms * 8, 128, 0, st>>>(sc, job, wb, wb.stats);
             wf_phase_kernel<<<1, 32, 0, st>>>(wb, 1, nullptr);
             wf_shade_kernel<true><<<sms * 8, 128, 0, st>>>(sc, job, wb);
             wf_shade_kernel<false><<<sms * 8, 128, 0, st>>>(sc, job, wb);
@@ -249,6 +254,15 @@ int launch_wave(ptgpu_ctx* ctx, const Scene& sc, RenderJob job)
         if(*ctx->wave_flag_host == 0u || rounds >= max_rounds) break;
     }
     ctx->last_wave_rounds = rounds;
+    if(ctx->validate)
+    {
+        unsigned long long h = 0;
+        cudaMemcpyAsync(&h, wb.stats, sizeof(h), cudaMemcpyDeviceToHost, st);
+        cudaStreamSynchronize(st);
+        ctx->last_validate_mismatches = h;
+    }
+    ctx->last_wave_lanes = lanes;
+    ctx->last_pool_bytes = off;
 #ifdef WF_STATS
     {
         unsigned long long h[16];
@@ -818,6 +832,7 @@ int ptgpu_set_option(ptgpu_ctx* ctx, const char* key, int64_t value)
     if(!strcmp(key, "xform_threshold")) { if(value < 1 || value > 32) return fail(ctx, "xform_threshold must be 1..32"); ctx->xform_threshold = (int)value; return 0; }
     if(!strcmp(key, "node_threshold")) { if(value < 1 || value > 32) return fail(ctx, "node_threshold must be 1..32"); ctx->node_threshold = (int)value; return 0; }
     if(!strcmp(key, "node_burst")) { if(value < 1 || value > 64) return fail(ctx, "node_burst must be 1..64"); ctx->node_burst = (int)value; return 0; }
+    if(!strcmp(key, "validate")) { ctx->validate = value != 0; return 0; }
     if(!strcmp(key, "lanes")) { if(value < 1 || value > 4096 || (value & (value - 1))) return fail(ctx, "lanes must be a power of two in 1..4096"); ctx->max_lanes = (int)value; return 0; }
     if(!strcmp(key, "pool_budget_mb")) { if(value < 1) return fail(ctx, "pool_budget_mb must be positive"); ctx->pool_budget_bytes = (size_t)value << 20; return 0; }
     if(!strcmp(key, "min_active")) { if(value < -1 || value > 32) return fail(ctx, "min_active must be -1..32"); ctx->min_active = (int)value; return 0; }
@@ -872,6 +887,16 @@ int ptgpu_host_flatten_check(
     }
     if(err && err_len) { strncpy(err, e.c_str(), err_len - 1); err[err_len - 1] = 0; }
     return 1;
+}
+
+int ptgpu_get_stat(ptgpu_ctx* ctx, const char* key, uint64_t* out)
+{
+    if(!ctx || !key || !out) return 1;
+    if(!strcmp(key, "validate_mismatches")) { *out = ctx->last_validate_mismatches; return 0; }
+    if(!strcmp(key, "wave_rounds")) { *out = (uint64_t)ctx->last_wave_rounds; return 0; }
+    if(!strcmp(key, "wave_lanes")) { *out = ctx->last_wave_lanes; return 0; }
+    if(!strcmp(key, "pool_bytes")) { *out = ctx->last_pool_bytes; return 0; }
+    return fail(ctx, "unknown stat '%s'", key);
 }
 
 } // extern "C"

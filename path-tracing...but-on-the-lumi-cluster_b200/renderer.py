@@ -181,6 +181,11 @@ class Renderer:
         self._check(self.lib.ptgpu_read_counters(self.ctx, out), "ptgpu_read_counters")
         return {n: int(out[i]) for i, n in enumerate(CNT_NAMES)}
 
+    def get_stat(self, key):
+        out = C.c_uint64()
+        self._check(self.lib.ptgpu_get_stat(self.ctx, key.encode(), C.byref(out)), "ptgpu_get_stat")
+        return int(out.value)
+
     def scene_stats(self):
         out = (C.c_uint64 * 8)()
         self._check(self.lib.ptgpu_scene_stats(self.ctx, out), "ptgpu_scene_stats")

@@ -242,6 +242,34 @@ def test_edge_cases(frames, pkg):
     r2.close()
 
 
+def test_scheduled_traversal_equals_plain_traversal(frames):
+    """Every ray of every round re-traced with the plain single-ray traversal (option "validate"):
+    the burst-scheduled kernel (postponed triangle tests, parked instance groups) must store the same
+    hit. Frames 520 and 1000 contain the dragon/buddha meshes with degenerate triangles, which once
+    produced spurious, scheduling-dependent hits."""
+    for frame in (520, 1000):
+        r = frames.use(frame)
+        r.set_option("validate", 1)
+        try:
+            a, _ = r.render_rect(96, 240, 96, 64, 0, 64, 4, tonemap=False)
+            assert r.get_stat("validate_mismatches") == 0
+            assert r.get_stat("wave_lanes") == 64 and r.get_stat("wave_rounds") <= 8
+            # and the image does not depend on how the warps were scheduled
+            r.set_option("validate", 0)
+            for opts in ({"node_threshold": 1, "tri_threshold": 1, "xform_threshold": 1}, {"node_burst": 1, "min_active": 1}, {"lanes": 8}):
+                for k, v in opts.items():
+                    r.set_option(k, v)
+                b, _ = r.render_rect(96, 240, 96, 64, 0, 64, 4, tonemap=False)
+                if "lanes" in opts:   # another summation order over the samples: rounding-level differences
+                    np.testing.assert_allclose(a, b, rtol=2e-5, atol=1e-7)
+                else:
+                    assert np.array_equal(a, b), opts
+                for k, v in {"node_threshold": 12, "tri_threshold": 8, "xform_threshold": 4, "node_burst": 2, "min_active": -1, "lanes": 256}.items():
+                    r.set_option(k, v)
+        finally:
+            r.set_option("validate", 0)
+
+
 def test_full_size_properties(frames, oracle):
     """At BASELINE.json's full size (640x360x256 spp) the oracle is too slow to compare everything,
     so use size-independent properties: determinism (two runs bit-identical), linearity of the
