@@ -27,11 +27,14 @@ namespace pt {
 #define WF_SEG_SHADOW 2
 #define WF_NEED_SAMPLE (-1)   // cursor.y: the slot waits for wf_generate
 #define WF_FINISHED (-2)      // cursor.y: no samples left
+#define WF_ST_NONE 0          // status: nothing to shade
+#define WF_ST_NEAR 2          // status: closest-hit query done, 0 < t < 1e3 (no sky march, path_tracer.hh:513)
+#define WF_ST_FAR 3           // status: closest-hit query done, miss or t >= 1e3
 
 struct WaveCounters
 {
     uint32_t n_seg[3];                        // ray-queue segment extents: 0 bounce, 1 primary, 2 shadow
-    uint32_t n_far, n_near, n_new;            // result-queue extents; slots waiting for their next sample
+    uint32_t n_far, n_near, n_new;            // shade-queue extents; slots waiting for their next sample
     uint32_t cur_trace;                       // fetch cursor of wf_trace over the concatenated segments
     uint32_t pad;
 };
@@ -56,7 +59,8 @@ struct WaveBuffers
     // primary rays of neighbouring pixels stay together (coherent), sun-ward shadow rays share a
     // direction, bounce rays are incoherent anyway. Entry = slot | WF_SHADOW_BIT.
     uint32_t* q_trace;    // 3 segments of seg_cap entries
-    uint32_t* q_far;
+    uint8_t* status;      // per slot: WF_ST_*, written by wf_trace when a closest-hit query ends
+    uint32_t* q_far;      // shade queues, filled by wf_classify in slot order
     uint32_t* q_near;
     WaveCounters* cnt;
     unsigned long long* stats;   // WF_STATS builds only
@@ -96,6 +100,7 @@ __global__ void wf_init_kernel(WaveBuffers wb, RenderJob job)
     int lx, ly;
     const bool valid = slot_pixel(wb, job, slot, lx, ly) && (int)(slot & (wb.lanes - 1u)) < job.s_count;
     wb.sum[slot] = make_float4(0, 0, 0, 0);
+    wb.status[slot] = WF_ST_NONE;
     wb.cursor[slot] = make_int2((int)(slot & (wb.lanes - 1u)), valid ? WF_NEED_SAMPLE : WF_FINISHED);
     if(slot == 0)
     {
@@ -156,11 +161,8 @@ wf_trace_kernel(Scene sc, RenderJob job, WaveBuffers wb)
     // warp-uniform reserve of queue entries [res_base, res_base + res_n)
     uint32_t res_base = 0, res_n = 0;
     bool exhausted = false;
-    // warp-uniform output chunks (32 entries each) for the two result queues
-    uint32_t far_base = 0, far_fill = 32, near_base = 0, near_fill = 32;
 
     bool active = false;
-    int done_class = 0;               // 0 none, 1 near, 2 far (closest-hit query finished, not yet queued)
     uint32_t slot = 0;
     bool shadow_ray = false;
     uint32_t subframe = 0;
@@ -184,37 +186,6 @@ wf_trace_kernel(Scene sc, RenderJob job, WaveBuffers wb)
         // refill when at least job.min_active lanes are idle (or nothing is running)
         if(__popc(act) <= 32 - job.min_active || act == 0u)
         {
-            // -- queue finished closest-hit queries by class, in 32-entry chunks per warp --------------
-            #pragma unroll
-            for(int cls = 1; cls <= 2; ++cls)
-            {
-                const unsigned m = __ballot_sync(0xFFFFFFFFu, done_class == cls);
-                if(m == 0u) continue;
-                uint32_t& base = cls == 1 ? near_base : far_base;
-                uint32_t& fill = cls == 1 ? near_fill : far_fill;
-                uint32_t* q = cls == 1 ? wb.q_near : wb.q_far;
-                uint32_t* qn = cls == 1 ? &wb.cnt->n_near : &wb.cnt->n_far;
-                const uint32_t cnt = (uint32_t)__popc(m);
-                const uint32_t rank = (uint32_t)__popc(m & ((1u << lane) - 1u));
-                const uint32_t room = 32u - fill;
-                uint32_t new_base = 0;
-                if(cnt > room)
-                {
-                    if(lane == 0) new_base = atomicAdd(qn, 32u);
-                    new_base = __shfl_sync(0xFFFFFFFFu, new_base, 0);
-                }
-                if(done_class == cls)
-                {
-                    if(rank < room) q[base + fill + rank] = slot;
-                    else q[new_base + (rank - room)] = slot;
-                    done_class = 0;
-                }
-                if(cnt > room)
-                {
-                    base = new_base; fill = cnt - room;
-                }
-                else fill += cnt;
-            }
             // -- refill idle lanes from the ray queue ------------------------------------------------
             const unsigned idle = ~act;
             uint32_t want = (uint32_t)__popc(idle);
@@ -287,7 +258,7 @@ wf_trace_kernel(Scene sc, RenderJob job, WaveBuffers wb)
                 {
                     wb.hit[slot] = make_float4(hit.t, hit.u, hit.v, __uint_as_float(hit.inst));
                     wb.hit_prim[slot] = hit.prim | (hit.back_face ? 0x80000000u : 0u);
-                    done_class = (hit.t > 0.0f && hit.t < 1e3f) ? 1 : 2;
+                    wb.status[slot] = (hit.t > 0.0f && hit.t < 1e3f) ? WF_ST_NEAR : WF_ST_FAR;
                 }
             }
             else cur = stack[--sp];
@@ -363,10 +334,6 @@ wf_trace_kernel(Scene sc, RenderJob job, WaveBuffers wb)
             }
         }
     }
-    // pad the partly filled output chunks so that consumers can skip them (fill == 32 with no
-    // reservation is the initial state, so only chunks with fill < 32 exist and need padding)
-    if(near_fill < 32u && near_fill + lane < 32u) wb.q_near[near_base + near_fill + lane] = WF_INVALID;
-    if(far_fill < 32u && far_fill + lane < 32u) wb.q_far[far_base + far_fill + lane] = WF_INVALID;
 }
 
 // ---- trace on the compressed 8-wide BVH (pt_cwbvh.cuh): same queue protocol as wf_trace_kernel ------
@@ -393,10 +360,8 @@ wf_trace_cw_kernel(Scene sc, RenderJob job, WaveBuffers wb)
     const uint32_t n_entries = n_s0 + n_s1 + n_s2;
     uint32_t res_base = 0, res_n = 0;
     bool exhausted = false;
-    uint32_t far_base = 0, far_fill = 32, near_base = 0, near_fill = 32;
 
     bool active = false;
-    int done_class = 0;
     uint32_t slot = 0;
     __shared__ uint2 s_stack[CW_SM_STACK][WF_TRACE_THREADS];
     __shared__ uint2 s_pend[CW_PEND][WF_TRACE_THREADS];
@@ -412,34 +377,6 @@ wf_trace_cw_kernel(Scene sc, RenderJob job, WaveBuffers wb)
         const unsigned act = __ballot_sync(0xFFFFFFFFu, active);
         if(32 - __popc(act) >= job.min_active || act == 0u)
         {
-            // -- queue finished closest-hit queries by class, in 32-entry chunks per warp --------------
-            #pragma unroll
-            for(int cls = 1; cls <= 2; ++cls)
-            {
-                const unsigned m = __ballot_sync(0xFFFFFFFFu, done_class == cls);
-                if(m == 0u) continue;
-                uint32_t& base = cls == 1 ? near_base : far_base;
-                uint32_t& fill = cls == 1 ? near_fill : far_fill;
-                uint32_t* q = cls == 1 ? wb.q_near : wb.q_far;
-                uint32_t* qn = cls == 1 ? &wb.cnt->n_near : &wb.cnt->n_far;
-                const uint32_t cnt = (uint32_t)__popc(m);
-                const uint32_t rank = (uint32_t)__popc(m & ((1u << lane) - 1u));
-                const uint32_t room = 32u - fill;
-                uint32_t new_base = 0;
-                if(cnt > room)
-                {
-                    if(lane == 0) new_base = atomicAdd(qn, 32u);
-                    new_base = __shfl_sync(0xFFFFFFFFu, new_base, 0);
-                }
-                if(done_class == cls)
-                {
-                    if(rank < room) q[base + fill + rank] = slot;
-                    else q[new_base + (rank - room)] = slot;
-                    done_class = 0;
-                }
-                if(cnt > room) { base = new_base; fill = cnt - room; }
-                else fill += cnt;
-            }
             // -- refill idle lanes from the ray queue ------------------------------------------------
             const unsigned idle = ~act;
             const uint32_t want = (uint32_t)__popc(idle);
@@ -502,7 +439,7 @@ wf_trace_cw_kernel(Scene sc, RenderJob job, WaveBuffers wb)
                         {
                             wb.hit[slot] = make_float4(st.hit.t, st.hit.u, st.hit.v, __uint_as_float(st.hit.inst));
                             wb.hit_prim[slot] = st.hit.prim | (st.hit.back_face ? 0x80000000u : 0u);
-                            done_class = (st.hit.t > 0.0f && st.hit.t < 1e3f) ? 1 : 2;
+                            wb.status[slot] = (st.hit.t > 0.0f && st.hit.t < 1e3f) ? WF_ST_NEAR : WF_ST_FAR;
                         }
                     }
                 }
@@ -631,8 +568,6 @@ wf_trace_cw_kernel(Scene sc, RenderJob job, WaveBuffers wb)
             else { if(we) enter_step(); }
         }
     }
-    if(near_fill < 32u && near_fill + lane < 32u) wb.q_near[near_base + near_fill + lane] = WF_INVALID;
-    if(far_fill < 32u && far_fill + lane < 32u) wb.q_far[far_base + far_fill + lane] = WF_INVALID;
 }
 
 // ---- debug: re-trace every queue entry with the plain single-ray traversal and compare ---------------
@@ -673,6 +608,23 @@ __global__ void wf_validate_kernel(Scene sc, RenderJob job, WaveBuffers wb, unsi
                            slot, subframe, fo.x, fo.y, fo.z, fd.x, fd.y, fd.z, fo.w, fh.x, __float_as_uint(fh.w), hp & 0x7FFFFFFFu, h.t, h.inst, h.prim);
             }
         }
+    }
+}
+
+// ---- classify: slots whose closest-hit query finished -> the FAR / NEAR shade queues ------------------
+// wf_trace only writes a status byte per finished query; this scan appends the slots to the two
+// shade queues in slot order (= pixel order, the samples of a pixel adjacent), so the shade kernels
+// read the path state mostly coalesced and neighbouring lanes shade the same surface.
+__global__ void __launch_bounds__(256)
+wf_classify_kernel(WaveBuffers wb)
+{
+    const uint32_t rounded = (wb.n_slots + 31u) & ~31u;
+    for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < rounded; i += gridDim.x * blockDim.x)
+    {
+        const uint32_t status = i < wb.n_slots ? wb.status[i] : WF_ST_NONE;
+        if(status != WF_ST_NONE) wb.status[i] = WF_ST_NONE;
+        wf_append(wb.q_far, &wb.cnt->n_far, status == WF_ST_FAR, i);
+        wf_append(wb.q_near, &wb.cnt->n_near, status == WF_ST_NEAR, i);
     }
 }
 

@@ -189,21 +189,19 @@ int launch_wave(ptgpu_ctx* ctx, const Scene& sc, RenderJob job)
     const int tiles_x = (job.w + WF_TILE - 1) / WF_TILE, tiles_y = (job.h + WF_TILE - 1) / WF_TILE;
     // slots per pixel: the largest power of two <= the sample count that keeps the pool in budget
     const size_t n_pix_padded = (size_t)tiles_x * tiles_y * WF_TILE * WF_TILE;
-    const size_t bytes_per_slot = 16 * 9 + 4 + 8 + 4 + 5 * 4;
+    const size_t bytes_per_slot = 16 * 9 + 4 + 8 + 4 + 5 * 4 + 1;
     uint32_t lanes = 1, lane_shift = 0;
     while(lanes * 2 <= (uint32_t)job.s_count && lanes * 2 <= (uint32_t)ctx->max_lanes &&
           n_pix_padded * (lanes * 2) * bytes_per_slot <= ctx->pool_budget_bytes && n_pix_padded * (lanes * 2) < 0x7FFF0000ull)
     { lanes *= 2; lane_shift++; }
     const uint32_t n_slots = (uint32_t)(n_pix_padded * lanes);
-    const size_t q_pad = 32u * 1024u * 16u;
     size_t off = 0;
     auto carve = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~size_t(255); return o; };
     const size_t o_rng = carve(16ull * n_slots), o_ro = carve(16ull * n_slots), o_rd = carve(16ull * n_slots),
         o_sd = carve(16ull * n_slots), o_hit = carve(16ull * n_slots), o_prim = carve(4ull * n_slots),
         o_att = carve(16ull * n_slots), o_con = carve(16ull * n_slots), o_nee = carve(16ull * n_slots),
         o_sum = carve(16ull * n_slots), o_cur = carve(8ull * n_slots), o_vis = carve(4ull * n_slots),
-        o_qt = carve(4ull * 3ull * (n_slots + 64)), o_qf = carve(4ull * (n_slots + q_pad)),
-        o_qn = carve(4ull * (n_slots + q_pad)), o_cnt = carve(sizeof(WaveCounters)), o_stats = carve(16 * 8);
+        o_qt = carve(4ull * 3ull * (n_slots + 64)), o_st = carve(n_slots), o_qf = carve(4ull * (n_slots + 64)), o_qn = carve(4ull * (n_slots + 64)), o_cnt = carve(sizeof(WaveCounters)), o_stats = carve(16 * 8);
     if(ctx->wave_mem.reserve(off) != cudaSuccess) return -1;
     if(!ctx->wave_flag_host)
     {
@@ -216,7 +214,8 @@ int launch_wave(ptgpu_ctx* ctx, const Scene& sc, RenderJob job)
     wb.shadow_d = (float4*)(m + o_sd); wb.hit = (float4*)(m + o_hit); wb.hit_prim = (uint32_t*)(m + o_prim);
     wb.atten = (float4*)(m + o_att); wb.contrib = (float4*)(m + o_con); wb.nee = (float4*)(m + o_nee);
     wb.sum = (float4*)(m + o_sum); wb.cursor = (int2*)(m + o_cur); wb.visible = (uint32_t*)(m + o_vis);
-    wb.q_trace = (uint32_t*)(m + o_qt); wb.q_far = (uint32_t*)(m + o_qf); wb.q_near = (uint32_t*)(m + o_qn);
+    wb.q_trace = (uint32_t*)(m + o_qt); wb.status = m + o_st;
+    wb.q_far = (uint32_t*)(m + o_qf); wb.q_near = (uint32_t*)(m + o_qn);
     wb.cnt = (WaveCounters*)(m + o_cnt);
     wb.stats = (unsigned long long*)(m + o_stats);
     wb.n_slots = n_slots; wb.seg_cap = n_slots + 64; wb.tiles_x = tiles_x;
@@ -244,10 +243,11 @@ int launch_wave(ptgpu_ctx* ctx, const Scene& sc, RenderJob job)
             else wf_trace_kernel<<<sms * 6, WF_TRACE_THREADS, 0, st>>>(sc, job, wb);
             if(ctx->validate && ctx->bvh == 1) wf_validate_kernel<<<sms * 8, 128, 0, st>>>(sc, job, wb, wb.stats);
             wf_phase_kernel<<<1, 32, 0, st>>>(wb, 1, nullptr);
+            wf_classify_kernel<<<sms * 8, 256, 0, st>>>(wb);
             wf_shade_kernel<true><<<sms * 8, 128, 0, st>>>(sc, job, wb);
             wf_shade_kernel<false><<<sms * 8, 128, 0, st>>>(sc, job, wb);
             wf_phase_kernel<<<1, 32, 0, st>>>(wb, 2, ctx->wave_flag.p);
-            launches += 6;
+            launches += 7;
         }
         if(cudaMemcpyAsync(ctx->wave_flag_host, ctx->wave_flag.p, 4, cudaMemcpyDeviceToHost, st) != cudaSuccess) return -1;
         if(cudaStreamSynchronize(st) != cudaSuccess) return -1;
