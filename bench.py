@@ -159,7 +159,7 @@ def workload_config(n_gpus):
     return {"workload": "full default animation, config.hh TESTING size: 640x360, 256 spp, 4 bounces, 32 motion-blur subframes; "
                         "one step = one frame (58,982,400 paths); steps cycle 14 snapshot frames spread over the 1800-frame animation",
             "frames_per_step": 1, "paths_per_step": PATHS_PER_FRAME, "parallelism": "frames sharded over %d GPU(s), no collective" % n_gpus,
-            "l2_policy": "inputs larger than L2 are not needed: every step renders a different frame and rewrites the 295 MB path-state pool (> 126 MB L2)"}
+            "l2_policy": "every step renders a different frame and streams the 10.9 GB path-state pool (one slot per path) through HBM, far larger than the 126 MB L2"}
 
 
 def main():

@@ -27,8 +27,13 @@
 #include <unistd.h>
 #include <omp.h>
 
+/* scene.cc:62-74 — external linkage, but not declared in scene.hh */
+void add_instance(scene& s, const char* name, float3 pos, float3 pitch_yaw_roll, float3 scale);
+
 namespace {
 std::unique_ptr<scene> g_scene;
+std::vector<tlas_instance> g_saved_instances; /* the 885 static instances while the stress scene is set up */
+uint g_saved_static_count = 0;
 }
 
 extern "C" {
@@ -220,6 +225,74 @@ void ref_trace_closest(const float o[3], const float d[3], float tmin, float tma
     out_u[0] = rq.closest.instance_id;
     out_u[1] = rq.closest.primitive_id;
     out_u[2] = rq.closest.back_face ? 1u : 0u;
+}
+
+/* BASELINE.json configs[3], SURVEY.md 8(d) "config 4": a synthetic high-poly stress frame built through
+ * the reference's own host API — buddha (54,384 tris), dragon (43,569) and armadillo (34,594) side by
+ * side above the terrain, one fixed camera framing all three, the sun at its frame-600 elevation
+ * (scene.cc:691-693), no motion: the same subframe replicated ceil(SPP/8) times, one TLAS (terrain +
+ * the three meshes). Fixed transforms; `ref_restore_scene` brings the animation scene back. */
+int ref_setup_stress_scene()
+{
+    if(!g_scene) return 1;
+    scene& s = *g_scene;
+    if(s.subframes.size() != 0) pop_bvh(s.bvh_buf, s.subframes[0].tlas); /* scene.cc:274-275 */
+    s.subframes.clear();
+    if(g_saved_instances.empty())
+    {
+        g_saved_instances.assign(s.instances.begin(), s.instances.begin() + s.static_instance_count);
+        g_saved_static_count = s.static_instance_count;
+    }
+    s.instances.resize(1);          /* instance 0 is the terrain (scene.cc:184) */
+    s.static_instance_count = 1;
+    add_instance(s, "buddha", float3{-5.5f, 19.5f, 0.0f}, float3{0, 20, 0}, float3{1, 1, 1});
+    add_instance(s, "dragon", float3{0.0f, 19.0f, 0.0f}, float3{0, 200, 0}, float3{1, 1, 1});
+    add_instance(s, "armadillo", float3{5.5f, 20.5f, 0.0f}, float3{0, 170, 0}, float3{1, 1, 1});
+
+    camera cam;
+    cam.position = float3{0.0f, 23.0f, 10.0f};
+    cam.aspect_ratio = IMAGE_WIDTH / float(IMAGE_HEIGHT);
+    cam.focal_distance = 2.0f;
+    cam.aperture_angle = M_PI / 16.0f;
+    cam.aperture_polygon = 6;
+    cam.aperture_radius = 0.0f;
+    cam.orientation = extract_m4m3(rotation_euler(float3{-12.0f, 0.0f, 0.0f} * M_PI / 180.0f));
+    cam.inv_focal_length = tan(60.0f * M_PI / 360.0f);
+    directional_light light;
+    light.color = float3{4, 4, 4};
+    light.cos_solid_angle = cos(4.0f * M_PI / 180.0f);
+    float sunset_t = 600.0f / (30.0f * 60.0f) * 1.1f - 0.05f;
+    light.direction = float3{0, sinf(sunset_t * M_PI), cosf(sunset_t * M_PI)};
+
+    std::vector<std::pair<const tlas_instance*, uint>> list;
+    for(uint i = 0; i < s.instances.size(); ++i) list.push_back({&s.instances[i], i});
+    bvh_buffers local;
+    bvh tlas = build_tlas(list.size(), list.data(), s.bvh_buf, local);
+    tlas.node_offset = s.bvh_buf.nodes.size();
+    s.bvh_buf.nodes.insert(s.bvh_buf.nodes.end(), local.nodes.begin(), local.nodes.end());
+    s.bvh_buf.links.insert(s.bvh_buf.links.end(), local.links.begin(), local.links.end());
+    uint subframe_count = (SAMPLES_PER_PIXEL + SAMPLES_PER_MOTION_BLUR_STEP - 1) / SAMPLES_PER_MOTION_BLUR_STEP;
+    for(uint i = 0; i < subframe_count; ++i)
+    {
+        subframe sf;
+        sf.tlas = tlas;
+        sf.cam = cam;
+        sf.light = light;
+        s.subframes.push_back(sf);
+    }
+    return 0;
+}
+
+int ref_restore_scene()
+{
+    if(!g_scene || g_saved_instances.empty()) return 1;
+    scene& s = *g_scene;
+    if(s.subframes.size() != 0) pop_bvh(s.bvh_buf, s.subframes[0].tlas);
+    s.subframes.clear();
+    s.instances = g_saved_instances;
+    s.static_instance_count = g_saved_static_count;
+    g_saved_instances.clear();
+    return 0;
 }
 
 void ref_write_bmp(const char* name, uint32_t w, uint32_t h, const uint8_t* bgra)

@@ -102,6 +102,8 @@ class Oracle:
         L.ref_trace_closest.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_float,
                                         C.c_float, C.c_uint32, C.POINTER(C.c_float),
                                         C.POINTER(C.c_uint32)]
+        L.ref_setup_stress_scene.restype = C.c_int
+        L.ref_restore_scene.restype = C.c_int
         L.ref_write_bmp.argtypes = [C.c_char_p, C.c_uint32, C.c_uint32, C.c_void_p]
         self.config = RefConfig()
         L.ref_get_config(C.byref(self.config))
@@ -122,6 +124,19 @@ class Oracle:
         self.lib.ref_setup_frame(int(frame))
         self.frame = int(frame)
         return self.view()
+
+    def setup_stress_scene(self):
+        """BASELINE.json configs[3]: terrain + buddha + dragon + armadillo, fixed camera (ref_harness.cc).
+        The view then has 1 static instance and 3 dynamic ones. Call restore_scene() afterwards."""
+        self.load_scene()
+        if self.lib.ref_setup_stress_scene() != 0:
+            raise RuntimeError("ref_setup_stress_scene failed")
+        self.frame = "stress"
+        return self.view()
+
+    def restore_scene(self):
+        self.lib.ref_restore_scene()
+        self.frame = None
 
     def frame_count(self):
         return int(self.lib.ref_frame_count())

@@ -19,7 +19,9 @@ FRAME_KEYS = ("subframes", "dyn_instances", "tlas_nodes", "tlas_links")
 
 
 def static_path(tag="testing"):
-    return os.path.join(CACHE, "static_%s.npz" % tag)
+    """The static arrays do not depend on config.hh (resolution/spp only enter the per-frame camera and
+    the subframe count), so every config shares the one snapshot."""
+    return os.path.join(CACHE, "static_testing.npz")
 
 
 def frame_path(frame, tag="testing"):

@@ -270,6 +270,78 @@ def test_scheduled_traversal_equals_plain_traversal(frames):
             r.set_option("validate", 0)
 
 
+def _variant_case(pkg, variant, cfg, frame, window, samples):
+    from oracle import refbind
+    if not refbind.available(variant):
+        pytest.skip("oracle variant %s not built" % variant)
+    o = refbind.get(variant)
+    o.load_scene()
+    view = o.setup_frame(frame)
+    assert (o.config.width, o.config.height, o.config.spp, o.config.max_bounces) == (cfg.width, cfg.height, cfg.spp, cfg.max_bounces)
+    r = pkg.Renderer(cfg, device=0)
+    try:
+        r.upload_static(**pkg.scene_io.static_from_view(view))
+        r.set_frame(**pkg.scene_io.frame_from_view(view))
+        x0, y0, w, h = window
+        s_begin, s_count, s_stride = samples
+        g_rgb, g_bgra = r.render_rect(x0, y0, w, h, s_begin, s_count, s_stride)
+        o_rgb, o_bgra = o.render_rect(x0, y0, w, h, s_begin, s_count, s_stride)
+        ms, _ = r.last_render_ms()
+    finally:
+        r.close()
+    return mae255(g_bgra, o_bgra), mean_rel(g_rgb, o_rgb), ms, view["subframes"].shape[0]
+
+
+@pytest.mark.parametrize("frame", [376, 1100])
+def test_motion_blur_config_1024spp(pkg, frame):
+    """BASELINE.json configs[4]: motion-blur-heavy frames at 4x spp (1024 spp = 128 subframes per
+    frame, scene.cc:648-650): frame 376 is inside the 97-degree camera whip-pan (scene.cc:382-383),
+    frame 1100 in the bunny dash (scene.cc:541-563). 16 samples spread over all 128 subframes."""
+    cfg = pkg.Config.testing()
+    cfg.spp = 1024
+    mae, rel, ms, n_sub = _variant_case(pkg, "mb", cfg, frame, (160, 90, 320, 180), (0, 16, 64))
+    print("motion blur frame %d (128 subframes): MAE %.4f/255, image-mean rel %.2e, %.2f ms" % (frame, mae, rel, ms))
+    assert n_sub == 128
+    assert mae <= 1.0 and rel <= 2e-3
+
+
+def test_high_poly_stress_scene(pkg, oracle):
+    """BASELINE.json configs[3]: buddha + dragon + armadillo (132,547 triangles) side by side above the
+    terrain, built through the reference's own add_instance/build_tlas (oracle/ref_harness.cc), one
+    static instance and three dynamic ones through the C ABI; parity on a window + full-frame timing."""
+    view = oracle.setup_stress_scene()
+    try:
+        assert view["n_static_instances"] == 1 and view["instances"].shape[0] == 4
+        r = pkg.Renderer(pkg.Config.testing(), device=0)
+        try:
+            r.upload_static(**pkg.scene_io.static_from_view(view))
+            r.set_frame(**pkg.scene_io.frame_from_view(view))
+            x0, y0, w, h = 80, 100, 480, 240
+            g_rgb, g_bgra = r.render_rect(x0, y0, w, h, 0, 16, 16)
+            o_rgb, o_bgra = oracle.render_rect(x0, y0, w, h, 0, 16, 16)
+            mae, rel = mae255(g_bgra, o_bgra), mean_rel(g_rgb, o_rgb)
+            r.render_async(); r.sync()
+            r.render_async(); r.sync()
+            ms, _ = r.last_render_ms()
+            print("stress scene: MAE %.4f/255, image-mean rel %.2e; full frame 640x360x256: %.1f ms = %.1f Mpaths/s"
+                  % (mae, rel, ms, 640 * 360 * 256 / ms / 1e3))
+            assert mae <= 1.0 and rel <= 1e-3
+        finally:
+            r.close()
+    finally:
+        oracle.restore_scene()
+
+
+def test_production_config_window(pkg):
+    """The production settings of config.hh:21-25 (1920x1080, 1024 spp, 5 bounces): a 384x216 window
+    of frame 520, 8 samples spread over the 128 subframes, against the oracle built at that config."""
+    cfg = pkg.Config.production()
+    mae, rel, ms, n_sub = _variant_case(pkg, "prod", cfg, 520, (768, 432, 384, 216), (0, 8, 128))
+    print("production frame 520 window: MAE %.4f/255, image-mean rel %.2e, %.2f ms" % (mae, rel, ms))
+    assert n_sub == 128
+    assert mae <= 1.0 and rel <= 2e-3
+
+
 def test_full_size_properties(frames, oracle):
     """At BASELINE.json's full size (640x360x256 spp) the oracle is too slow to compare everything,
     so use size-independent properties: determinism (two runs bit-identical), linearity of the
