@@ -342,6 +342,28 @@ def test_production_config_window(pkg):
     assert mae <= 1.0 and rel <= 2e-3
 
 
+def test_validator_on_full_frames(frames, oracle):
+    """validator.py's rule (restated in oracle/validator_np.py) on whole frames at the full 256 spp: the
+    oracle-rendered frame is turned into the half-size reference PNG array the validator expects, the
+    GPU frame goes through ptgpu_render_bmp + the BMP reader. No BAD frame, MAE <= 1/255. Frame 0 is
+    cheap for the oracle (black sky); frame 1750 is the end card at dusk."""
+    from helpers import read_bmp_rgb
+    from oracle import validator_np as V
+    import tempfile
+    for frame in (0, 1750):
+        r = frames.use(frame)
+        bmp = r.render_bmp()
+        with tempfile.NamedTemporaryFile(suffix=".bmp") as f:
+            f.write(bmp.tobytes()); f.flush()
+            own = read_bmp_rgb(f.name)
+        _, o_bgra = oracle.render_frame()
+        ref_rgb = o_bgra[..., 2::-1]
+        psnr, good = V.validate_frame(V.make_reference_png_array(ref_rgb), own)
+        mae = np.abs(own.astype(np.float64) - ref_rgb.astype(np.float64)).mean()
+        print("validator frame %04d: PSNR %.2f dB %s, full-frame MAE %.4f/255" % (frame, psnr, "GOOD" if good else "BAD", mae))
+        assert good and mae <= 1.0
+
+
 def test_full_size_properties(frames, oracle):
     """At BASELINE.json's full size (640x360x256 spp) the oracle is too slow to compare everything,
     so use size-independent properties: determinism (two runs bit-identical), linearity of the
