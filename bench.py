@@ -155,9 +155,11 @@ def frame_list():
     return frames
 
 
-def workload_config(n_gpus):
+def workload_config(n_gpus, animation=False):
     return {"workload": "full default animation, config.hh TESTING size: 640x360, 256 spp, 4 bounces, 32 motion-blur subframes; "
-                        "one step = one frame (58,982,400 paths); steps cycle 14 snapshot frames spread over the 1800-frame animation",
+                        "one step = one frame (58,982,400 paths); " + (
+                            "steps walk the 1800-frame animation at a uniform stride" if animation else
+                            "steps cycle 14 frames spread over the 1800-frame animation (0,100,200,330,420,520,660,800,1000,1100,1250,1400,1600,1750)"),
             "frames_per_step": 1, "paths_per_step": PATHS_PER_FRAME, "parallelism": "frames sharded over %d GPU(s), no collective" % n_gpus,
             "l2_policy": "every step renders a different frame and streams the 10.9 GB path-state pool (one slot per path) through HBM, far larger than the 126 MB L2"}
 
@@ -170,6 +172,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--kernel", type=int, default=None, help="0 megakernel, 1 tiles, 2 wavefront (default)")
+    ap.add_argument("--animation", action="store_true",
+                    help="walk the animation itself: step i renders frame (i*N + rank) * 1800 / (steps*N) through the "
+                         "frame-setup module (--steps 1800 --gpus 1 = every frame); no roofline (flops are frozen for the 14 snapshot frames)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -201,12 +206,23 @@ def main():
     r.upload_static(**sio.load_static(sio.static_path("testing")))
     snaps = {f: sio.load_frame(sio.frame_path(f, "testing")) for f in frames}
 
+    # per-frame scene state from the frame-setup module (csrc/frame_setup.cu): keyframe replay on the
+    # host, ~30 KB up, no reference TLAS arrays
+    anim = pkg.Animation(cfg) if os.path.exists(pkg.animation.default_path()) else None
+    if args.animation and anim is None:
+        raise SystemExit("bench.py: --animation needs scenes/_cache/animation.json (run __graft_entry__.build() where the reference is mounted)")
+
     def frame_of(step):
+        if args.animation:
+            return ((step * world + rank) * ANIMATION_FRAMES) // (args.steps * world)
         return frames[(step * world + rank) % len(frames)]
 
     def set_frame(f):
-        s = snaps[f]
-        r.set_frame(s["subframes"], s["dyn_instances"], s["tlas_nodes"], s["tlas_links"])
+        if anim is not None:
+            anim.set_frame(r, f)
+        else:
+            s = snaps[f]
+            r.set_frame(s["subframes"], s["dyn_instances"], s["tlas_nodes"], s["tlas_links"])
 
     def barrier():
         if dist is not None:
@@ -249,7 +265,14 @@ def main():
     t0 = time.perf_counter()
     h2d = 0
     for i in range(args.steps):
-        s = snaps[frame_of(i)]
+        f = frame_of(i)
+        if args.animation:
+            sub, dyn, db, de = anim.frame(f)                       # host: keyframe replay
+            r.set_frame_ranges(sub, dyn, db, de)                   # host arrays -> device
+            r.render(out=out_np)                                   # render + BGRA frame back to pinned host memory
+            h2d += sub.nbytes + dyn.nbytes + dyn.shape[0] * 128 + sub.shape[0] * 8
+            continue
+        s = snaps[f]
         r.render_frame(s["subframes"], s["dyn_instances"], s["tlas_nodes"], s["tlas_links"], out=out_np)
         h2d += s["subframes"].nbytes + s["dyn_instances"].nbytes + (s["dyn_instances"].shape[0] * 128) + s["subframes"].shape[0] * 8
     barrier()
@@ -273,7 +296,7 @@ def main():
         sm_max = float(peaks.get("sm_max_mhz", 1965.0))
         peak_tflops = 148 * 128 * 2 * sm_max * 1e6 / 1e12   # FP32 FMA issue peak
         # roofline on the device time of ONE rank's frames (max over ranks), flops of all ranks / world
-        achieved = (flops / world) / dev_s / 1e12 if dev_s > 0 and flops > 0 else None
+        achieved = (flops / world) / dev_s / 1e12 if dev_s > 0 and flops > 0 and not args.animation else None
         prof = load_json(os.path.join(ROOT, "profiles", "roofline_inputs.json"), {}) or {}
         line = {
             "metric": "Mpaths/s", "value": round(value, 2), "unit": "Mpaths/s",
@@ -281,12 +304,13 @@ def main():
             "ms_per_step": round(1e3 * wall_a / args.steps, 3), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32",
             "data": "synthetic (reference animation via scene snapshots; stand-in terrain/pine/bunny assets)",
-            "config": workload_config(world),
+            "config": workload_config(world, args.animation),
             "animation_seconds_estimate": round(ANIMATION_FRAMES * (wall_a / args.steps) / world, 1),
             "device_ms_per_step": round(1e3 * dev_s / args.steps, 3),
             "e2e": {"value": round(e2e, 2), "unit": "Mpaths/s", "h2d_bytes_per_step": int(h2d / args.steps),
                     "d2h_bytes_per_step": WIDTH * HEIGHT * 4, "ms_per_step": round(1e3 * wall_b / args.steps, 3),
-                    "call": "ptgpu_render_frame (include/ptgpu.h)"},
+                    "call": "ptgpu_anim_frame + ptgpu_set_frame_ranges + ptgpu_render" if args.animation else "ptgpu_render_frame (include/ptgpu.h)"},
+            "frame_setup": "ptgpu_set_animation_frame (csrc/frame_setup.cu)" if anim is not None else "snapshot arrays via ptgpu_set_frame",
             "gpu_launches": int(launches),
             "clocks": sampler.result(),
             "roofline": {"bound": "fp32", "achieved": round(achieved, 3) if achieved else None, "peak": round(peak_tflops, 2),

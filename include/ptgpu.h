@@ -223,6 +223,48 @@ int ptgpu_read_counters(ptgpu_ctx* ctx, uint64_t out[PTGPU_CNT_COUNT]);
  * wide-BVH nodes, triangles, static instances}. */
 int ptgpu_scene_stats(ptgpu_ctx* ctx, uint64_t out[8]);
 
+/* ---- per-frame scene state without setup_animation_frame ------------------------ */
+
+/* The reference's setup_animation_frame (scene.cc:271-718) replays a keyframe table per motion-blur
+ * subframe, appends the dynamic instances and builds one SAH TLAS per subframe (75 ms per frame on one
+ * core). This library never needs those TLASes, so the per-frame host work is only the replay: these
+ * entry points restate it (csrc/frame_setup.cu) on top of DATA the caller hands in — the rows of the
+ * reference's `animation_stop anim[]` table (scene.cc:24-31, 319-627; the float* target replaced by a
+ * variable index) and the (mesh, bvh) handles of the seven dynamic meshes (scene.hh:49). */
+enum ptgpu_anim_var {
+    PTGPU_VAR_LOGO_VISIBLE, PTGPU_VAR_ARMADILLO_VISIBLE, PTGPU_VAR_DRAGON_VISIBLE, PTGPU_VAR_BUNNY_VISIBLE, PTGPU_VAR_END_VISIBLE,
+    PTGPU_VAR_CAM_POS_X, PTGPU_VAR_CAM_POS_Y, PTGPU_VAR_CAM_POS_Z, PTGPU_VAR_CAM_ORI_X, PTGPU_VAR_CAM_ORI_Y, PTGPU_VAR_CAM_ORI_Z,
+    PTGPU_VAR_FOV, PTGPU_VAR_FOCAL_DISTANCE, PTGPU_VAR_APERTURE_RADIUS,
+    PTGPU_VAR_TEAPOT_POS_X, PTGPU_VAR_TEAPOT_POS_Y, PTGPU_VAR_TEAPOT_POS_Z, PTGPU_VAR_TEAPOT_ORI_X, PTGPU_VAR_TEAPOT_ORI_Y, PTGPU_VAR_TEAPOT_ORI_Z,
+    PTGPU_VAR_ARMADILLO_POS_X, PTGPU_VAR_ARMADILLO_POS_Y, PTGPU_VAR_ARMADILLO_POS_Z, PTGPU_VAR_ARMADILLO_ORI_X, PTGPU_VAR_ARMADILLO_ORI_Y, PTGPU_VAR_ARMADILLO_ORI_Z,
+    PTGPU_VAR_DRAGON_POS_X, PTGPU_VAR_DRAGON_POS_Y, PTGPU_VAR_DRAGON_POS_Z, PTGPU_VAR_DRAGON_ORI_X, PTGPU_VAR_DRAGON_ORI_Y, PTGPU_VAR_DRAGON_ORI_Z,
+    PTGPU_VAR_BUNNY_POS_X, PTGPU_VAR_BUNNY_POS_Y, PTGPU_VAR_BUNNY_POS_Z, PTGPU_VAR_BUNNY_ORI_X, PTGPU_VAR_BUNNY_ORI_Y, PTGPU_VAR_BUNNY_ORI_Z,
+    PTGPU_VAR_END_POS_X, PTGPU_VAR_END_POS_Y, PTGPU_VAR_END_POS_Z, PTGPU_VAR_END_ORI_X, PTGPU_VAR_END_ORI_Y, PTGPU_VAR_END_ORI_Z,
+    PTGPU_ANIM_VAR_COUNT
+};
+enum ptgpu_anim_mesh {
+    PTGPU_MESH_LOGO, PTGPU_MESH_BUDDHA, PTGPU_MESH_TEAPOT, PTGPU_MESH_ARMADILLO, PTGPU_MESH_DRAGON, PTGPU_MESH_BUNNY, PTGPU_MESH_END,
+    PTGPU_MESH_COUNT
+};
+typedef struct { float start, duration, from, to; int32_t var; } ptgpu_anim_key;   /* animation_stop, scene.cc:24-31 */
+typedef struct { ptgpu_mesh m; ptgpu_bvh blas; } ptgpu_mesh_handle;                /* scene::meshes entry, scene.hh:49 */
+typedef struct ptgpu_anim ptgpu_anim;
+
+int ptgpu_anim_create(ptgpu_anim** out, const ptgpu_anim_key* keys, size_t n_keys,
+                      const ptgpu_mesh_handle* meshes /* [PTGPU_MESH_COUNT] */, const ptgpu_config* cfg);
+void ptgpu_anim_destroy(ptgpu_anim* anim);
+size_t ptgpu_anim_subframe_count(const ptgpu_anim* anim);   /* ceil(spp / 8), scene.cc:648-650 */
+size_t ptgpu_anim_max_instances(const ptgpu_anim* anim);    /* capacity needed for `dyn` below */
+uint32_t ptgpu_anim_frame_count(const ptgpu_anim* anim);    /* get_animation_frame_count, scene.cc:720-724 */
+/* What setup_animation_frame(s, frame) leaves in s.subframes and s.instances[static_instance_count..),
+ * minus the TLAS handles: subframes[subframe_count] (tlas zeroed), dyn[*n_dyn], and each subframe's
+ * range [dyn_begin[i], dyn_end[i]) of per-subframe instances (scene.cc:651-678); the instances before
+ * the first range are the frame-static extras (logo, buddha). Pure function of `frame`: re-entrant. */
+int ptgpu_anim_frame(const ptgpu_anim* anim, uint32_t frame, ptgpu_subframe* subframes,
+                     ptgpu_tlas_instance* dyn, size_t* n_dyn, uint32_t* dyn_begin, uint32_t* dyn_end);
+/* ptgpu_anim_frame + ptgpu_set_frame_ranges */
+int ptgpu_set_animation_frame(ptgpu_ctx* ctx, const ptgpu_anim* anim, uint32_t frame);
+
 /* Facts about the most recent wavefront render: "wave_rounds", "wave_lanes" (path slots per pixel),
  * "pool_bytes" (path-state pool), "validate_mismatches" (with option "validate" = 1 every ray of
  * every round is re-traced with the plain single-ray traversal and compared with what the scheduled

@@ -9,3 +9,4 @@ from .renderer import Renderer  # noqa: F401
 from . import scene_io  # noqa: F401
 from . import sharding  # noqa: F401
 from . import capi  # noqa: F401
+from .animation import Animation  # noqa: F401

@@ -16,6 +16,8 @@ SYMBOLS = [
     "ptgpu_pcg4d", "ptgpu_render_async", "ptgpu_fetch_bgra", "ptgpu_fetch_bmp", "ptgpu_sync",
     "ptgpu_last_render_ms", "ptgpu_set_option", "ptgpu_read_counters", "ptgpu_scene_stats",
     "ptgpu_host_flatten_check", "ptgpu_get_stat",
+    "ptgpu_anim_create", "ptgpu_anim_destroy", "ptgpu_anim_subframe_count", "ptgpu_anim_max_instances",
+    "ptgpu_anim_frame_count", "ptgpu_anim_frame", "ptgpu_set_animation_frame",
 ]
 
 
@@ -94,10 +96,22 @@ def load_library():
     L.ptgpu_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
     L.ptgpu_read_counters.argtypes = [vp, C.POINTER(C.c_uint64)]
     L.ptgpu_scene_stats.argtypes = [vp, C.POINTER(C.c_uint64)]
+    L.ptgpu_anim_create.argtypes = [C.POINTER(vp), vp, sz, vp, C.POINTER(Config)]
+    L.ptgpu_anim_destroy.argtypes = [vp]
+    L.ptgpu_anim_destroy.restype = None
+    L.ptgpu_anim_subframe_count.argtypes = [vp]
+    L.ptgpu_anim_subframe_count.restype = sz
+    L.ptgpu_anim_max_instances.argtypes = [vp]
+    L.ptgpu_anim_max_instances.restype = sz
+    L.ptgpu_anim_frame_count.argtypes = [vp]
+    L.ptgpu_anim_frame_count.restype = C.c_uint32
+    L.ptgpu_anim_frame.argtypes = [vp, C.c_uint32, vp, vp, C.POINTER(sz), vp, vp]
+    L.ptgpu_set_animation_frame.argtypes = [vp, vp, C.c_uint32]
     L.ptgpu_get_stat.argtypes = [vp, C.c_char_p, C.POINTER(C.c_uint64)]
     L.ptgpu_host_flatten_check.argtypes = [vp, sz, vp, sz, vp, sz, vp, sz, vp, sz, C.POINTER(C.c_uint64), C.c_char_p, sz]
     for name in SYMBOLS:
-        if name not in ("ptgpu_default_config", "ptgpu_destroy", "ptgpu_last_error", "ptgpu_bmp_size"):
+        if name not in ("ptgpu_default_config", "ptgpu_destroy", "ptgpu_last_error", "ptgpu_bmp_size", "ptgpu_anim_destroy",
+                        "ptgpu_anim_subframe_count", "ptgpu_anim_max_instances", "ptgpu_anim_frame_count"):
             getattr(L, name).restype = C.c_int
     _lib = L
     return L

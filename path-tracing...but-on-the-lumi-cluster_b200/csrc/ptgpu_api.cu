@@ -899,4 +899,18 @@ int ptgpu_get_stat(ptgpu_ctx* ctx, const char* key, uint64_t* out)
     return fail(ctx, "unknown stat '%s'", key);
 }
 
+int ptgpu_set_animation_frame(ptgpu_ctx* ctx, const ptgpu_anim* anim, uint32_t frame)
+{
+    if(!ctx) return 1;
+    if(!anim) return fail(ctx, "ptgpu_set_animation_frame: null animation");
+    const size_t n_sub = ptgpu_anim_subframe_count(anim);
+    std::vector<ptgpu_subframe> sub(n_sub);
+    std::vector<ptgpu_tlas_instance> dyn(ptgpu_anim_max_instances(anim));
+    std::vector<uint32_t> b(n_sub), e(n_sub);
+    size_t n_dyn = 0;
+    if(ptgpu_anim_frame(anim, frame, sub.data(), dyn.data(), &n_dyn, b.data(), e.data()) != 0)
+        return fail(ctx, "ptgpu_anim_frame failed");
+    return ptgpu_set_frame_ranges(ctx, sub.data(), n_sub, dyn.data(), n_dyn, b.data(), e.data());
+}
+
 } // extern "C"

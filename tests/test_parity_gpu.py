@@ -342,6 +342,29 @@ def test_production_config_window(pkg):
     assert mae <= 1.0 and rel <= 2e-3
 
 
+def test_animation_module_renders_the_same_frames(frames, oracle, pkg):
+    """N1: ptgpu_set_animation_frame (own keyframe replay, no reference TLAS) vs ptgpu_set_frame on what
+    the reference's setup_animation_frame produced: same picture (transforms agree to float rounding)."""
+    import os
+    if not os.path.exists(pkg.animation.default_path()):
+        pytest.skip("scenes/_cache/animation.json not built")
+    an = pkg.Animation(pkg.Config.testing())
+    for frame in (100, 1100):
+        r = frames.use(frame)
+        a_rgb, a_bgra = r.render_rect(160, 90, 320, 180, 0, 32, 8)
+        an.set_frame(r, frame)
+        frames.current = None
+        b_rgb, b_bgra = r.render_rect(160, 90, 320, 180, 0, 32, 8)
+        o_rgb, o_bgra = oracle.render_rect(160, 90, 320, 180, 0, 32, 8)
+        print("animation module frame %d: vs reference-arrays path MAE %.4f/255; vs oracle MAE %.4f/255, mean-rel %.2e"
+              % (frame, mae255(a_bgra, b_bgra), mae255(b_bgra, o_bgra), mean_rel(b_rgb, o_rgb)))
+        # the module's matrices agree with the reference's to float rounding (tests/test_animation_cpu.py);
+        # a last-bit difference can still flip individual paths, so the two renders are compared statistically
+        assert mae255(a_bgra, b_bgra) <= 1.0 and mean_rel(a_rgb, b_rgb) <= 2e-3
+        assert mae255(b_bgra, o_bgra) <= 1.0 and mean_rel(b_rgb, o_rgb) <= 2e-3
+    an.close()
+
+
 def test_validator_on_full_frames(frames, oracle):
     """validator.py's rule (restated in oracle/validator_np.py) on whole frames at the full 256 spp: the
     oracle-rendered frame is turned into the half-size reference PNG array the validator expects, the
