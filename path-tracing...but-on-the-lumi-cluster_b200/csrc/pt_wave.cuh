@@ -350,7 +350,7 @@ wf_trace_kernel(Scene sc, RenderJob job, WaveBuffers wb)
 constexpr int CW_PEND = 4;
 
 #ifndef WF_CW_BLOCKS
-#define WF_CW_BLOCKS 8
+#define WF_CW_BLOCKS 7
 #endif
 __global__ void __launch_bounds__(WF_TRACE_THREADS, WF_CW_BLOCKS)
 wf_trace_cw_kernel(Scene sc, RenderJob job, WaveBuffers wb)

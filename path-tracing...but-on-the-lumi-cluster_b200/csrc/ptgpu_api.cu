@@ -64,7 +64,7 @@ struct ptgpu_ctx
     int validate = 0;                          // debug: re-trace every ray with the plain traversal and compare
     int max_lanes = 256;                       // wavefront: slots per pixel (power of two)
     size_t pool_budget_bytes = 16ull << 30;    // wavefront: path-state pool budget
-    int tri_threshold = 8, xform_threshold = 4, node_threshold = 12, node_burst = 2;
+    int tri_threshold = 8, xform_threshold = 4, node_threshold = 16, node_burst = 2;
 
     // static scene, reference layout
     DevBuf<float2> ref_nodes;     // 3 per node; static region then per-frame TLAS region
