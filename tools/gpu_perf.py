@@ -16,8 +16,6 @@ def main():
     r = pkg.Renderer(cfg, 0)
     r.upload_static(**sio.load_static(sio.static_path()))
     variants = [("default", {"kernel": 2})]
-    for nt, nb, tt, xt, ma in ((12, 2, 8, 4, 4), (16, 2, 8, 4, 8), (8, 2, 6, 3, 8), (12, 3, 10, 4, 8), (12, 2, 8, 6, 8), (12, 1, 8, 4, 8)):
-        variants.append(("n%d b%d t%d x%d r%d" % (nt, nb, tt, xt, ma), {"kernel": 2, "min_active": ma, "node_threshold": nt, "node_burst": nb, "tri_threshold": tt, "xform_threshold": xt}))
     try:
         if os.environ.get("PTGPU_NO_ORACLE"): raise RuntimeError()
         from oracle import refbind
