@@ -51,6 +51,14 @@ def flops_table():
     return {int(k): v for k, v in t.get("frames", {}).items()}
 
 
+def traversal_flops_table():
+    """The traversal terms of the same formula (25 N_node + 56 N_tri + 61 N_blas + 9 N_ray): the
+    algorithmic flops of the dominant kernel, wf_trace_cw_kernel, per path."""
+    t = load_json(os.path.join(ROOT, "profiles", "flops_per_path.json"), {}) or {}
+    return {int(k): 25.0 * e["node_visits"] + 56.0 * e["tri_tests"] + 61.0 * e["blas_enters"] + 9.0 * e["rays"]
+            for k, e in t.get("events_per_path", {}).items()}
+
+
 class ClockSampler(threading.Thread):
     """Samples SM clock and throttle reasons with nvidia-smi while the timed region runs."""
 
@@ -247,7 +255,8 @@ def main():
     barrier()
     t0 = time.perf_counter()
     dev_ms, launches, flops = 0.0, 0, 0.0
-    ftab = flops_table()
+    trace_us, trace_launches, trace_flops = 0.0, 0, 0.0
+    ftab, ttab = flops_table(), traversal_flops_table()
     for i in range(args.steps):
         f = frame_of(i)
         set_frame(f)
@@ -256,6 +265,10 @@ def main():
         dev_ms += ms
         launches += n
         flops += ftab.get(f, 0.0) * PATHS_PER_FRAME
+        # the traversal launches of this frame, CUDA events on the render stream around each launch
+        trace_us += r.get_stat("trace_us")
+        trace_launches += r.get_stat("trace_launches")
+        trace_flops += ttab.get(f, 0.0) * PATHS_PER_FRAME
     barrier()
     wall_a = time.perf_counter() - t0
 
@@ -298,6 +311,9 @@ def main():
         # roofline on the device time of ONE rank's frames (max over ranks), flops of all ranks / world
         achieved = (flops / world) / dev_s / 1e12 if dev_s > 0 and flops > 0 and not args.animation else None
         prof = load_json(os.path.join(ROOT, "profiles", "roofline_inputs.json"), {}) or {}
+        # dominant kernel (rank 0's launches): algorithmic traversal flops / its own launch durations
+        k_ok = trace_us > 0 and trace_flops > 0 and trace_launches > 0 and not args.animation
+        k_achieved = trace_flops / (trace_us * 1e-6) / 1e12 if k_ok else None
         line = {
             "metric": "Mpaths/s", "value": round(value, 2), "unit": "Mpaths/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -316,6 +332,15 @@ def main():
             "roofline": {"bound": "fp32", "achieved": round(achieved, 3) if achieved else None, "peak": round(peak_tflops, 2),
                          "unit": "TFLOP/s", "frac": round(achieved / peak_tflops, 4) if achieved else None,
                          "traffic": prof.get("dram_bytes_per_frame"),
+                         "kernel": {"name": "wf_trace_cw_kernel", "launches": int(trace_launches),
+                                    "avg_launch_ms": round(trace_us / trace_launches / 1e3, 3) if k_ok else None,
+                                    "share_of_device_time": round(trace_us / 1e3 / dev_ms, 4) if k_ok and dev_ms > 0 else None,
+                                    "flops_per_launch": round(trace_flops / trace_launches, 0) if k_ok else None,
+                                    "achieved": round(k_achieved, 3) if k_ok else None,
+                                    "frac": round(k_achieved / peak_tflops, 4) if k_ok else None,
+                                    "traffic": prof.get("wf_trace_cw_dram_bytes_per_launch"),
+                                    "note": "traversal terms of the formula (25 N_node + 56 N_tri + 61 N_blas + 9 N_ray, reference BVH) / "
+                                            "CUDA-event time of the traversal launches on rank 0"},
                          "note": "whole frame (all kernels; wf_trace is %s of device time): algorithmic flops/path of SURVEY.md 8(d) "
                                  "from profiles/flops_per_path.json x paths / CUDA-event device time; peak = 148 SM x 128 lanes x 2 x %.0f MHz "
                                  "(sm_max_mhz of MEASURED_PEAKS.json); tensor cores unused; the path is not HBM-bound" % (

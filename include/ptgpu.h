@@ -268,7 +268,10 @@ int ptgpu_set_animation_frame(ptgpu_ctx* ctx, const ptgpu_anim* anim, uint32_t f
 /* Facts about the most recent wavefront render: "wave_rounds", "wave_lanes" (path slots per pixel),
  * "pool_bytes" (path-state pool), "validate_mismatches" (with option "validate" = 1 every ray of
  * every round is re-traced with the plain single-ray traversal and compared with what the scheduled
- * traversal kernel stored; the number of disagreeing queries). */
+ * traversal kernel stored; the number of disagreeing queries), "trace_us" / "shade_us" (device time
+ * of the traversal launches, and of the classify + shade launches, of that frame, from CUDA events
+ * recorded on the render stream around them; first 48 rounds) and "trace_launches" (how many
+ * traversal launches "trace_us" covers). */
 int ptgpu_get_stat(ptgpu_ctx* ctx, const char* key, uint64_t* out);
 
 /* Host-only, needs no GPU: runs the BVH flattening that ptgpu_upload_static performs on the

@@ -77,7 +77,21 @@ PT_D void cw_set_space(CwState& st, v3 o, v3 d)
     st.oct_inv4 = oct * 0x01010101u;
 }
 
-PT_D float u8f(uint32_t w, int j) { return (float)((w >> (8 * j)) & 0xFFu); }
+// Byte j of w as a float. I2F.U8 runs on the XU pipe (61 % busy in wf_trace_cw, 48 conversions per
+// node), so an exact ALU+FMA-pipe form was tried: PRMT builds 2^23 + b, one FADD removes the 2^23.
+// It is slower (CW_CVT 1: all 48 that way, +6 % frame time; 2: the near planes only, +1.4 %): the
+// kernel is bound by issue slots, not by the XU pipe, and the form costs one more instruction per byte.
+#ifndef CW_CVT
+#define CW_CVT 0
+#endif
+PT_D float u8f_xu(uint32_t w, int j) { return (float)((w >> (8 * j)) & 0xFFu); }
+PT_D float u8f_alu(uint32_t w, int j)
+{
+    return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7650u | (uint32_t)j)) - 8388608.0f;
+}
+// near-plane bytes and far-plane bytes may use different pipes (CW_CVT 2: near on ALU+FMA, far on XU)
+PT_D float u8f_near(uint32_t w, int j) { return CW_CVT >= 1 ? u8f_alu(w, j) : u8f_xu(w, j); }
+PT_D float u8f_far(uint32_t w, int j) { return CW_CVT == 1 ? u8f_alu(w, j) : u8f_xu(w, j); }
 
 // Box test of the eight children of one node; fills the node group (inner children hit) and the
 // leaf group (leaf payloads whose box was hit).
@@ -116,9 +130,9 @@ PT_D void cw_intersect_node(const float4* __restrict__ nodes, uint32_t node_inde
         #pragma unroll
         for(int j = 0; j < 4; ++j)
         {
-            const float t0x = fmaf(u8f(x_near, j), ax, ox), t1x = fmaf(u8f(x_far, j), ax, ox);
-            const float t0y = fmaf(u8f(y_near, j), ay, oy), t1y = fmaf(u8f(y_far, j), ay, oy);
-            const float t0z = fmaf(u8f(z_near, j), az, oz), t1z = fmaf(u8f(z_far, j), az, oz);
+            const float t0x = fmaf(u8f_near(x_near, j), ax, ox), t1x = fmaf(u8f_far(x_far, j), ax, ox);
+            const float t0y = fmaf(u8f_near(y_near, j), ay, oy), t1y = fmaf(u8f_far(y_far, j), ay, oy);
+            const float t0z = fmaf(u8f_near(z_near, j), az, oz), t1z = fmaf(u8f_far(z_far, j), az, oz);
             const float cmin = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, st.tmin));
             const float cmax = fminf(fminf(t1x, t1y), fminf(t1z, tmax_box));
             if(cmin <= cmax)

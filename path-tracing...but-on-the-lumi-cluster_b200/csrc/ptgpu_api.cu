@@ -108,6 +108,10 @@ struct ptgpu_ctx
     int last_wave_rounds = 0;
     uint32_t last_wave_lanes = 0;
     size_t last_pool_bytes = 0;
+    // per-kernel device time of the last wavefront frame (CUDA events on the render stream)
+    std::vector<cudaEvent_t> wave_events;
+    double last_trace_us = 0.0, last_shade_us = 0.0;
+    uint64_t last_trace_launches = 0;
     unsigned long long last_validate_mismatches = 0;
     uint32_t bmp_pitch = 0;
     bool bmp_header_done = false;
@@ -234,18 +238,29 @@ int launch_wave(ptgpu_ctx* ctx, const Scene& sc, RenderJob job)
     const int max_rounds = samples_per_slot * (sc.max_bounces + 1) + 2;
     const int check_every = 8;
     int rounds = 0;
+    // three events per round (trace begin, trace end, shade end) for the first WAVE_TIMED_ROUNDS rounds
+    const int WAVE_TIMED_ROUNDS = 48;
+    if(ctx->wave_events.empty())
+    {
+        ctx->wave_events.resize(3 * WAVE_TIMED_ROUNDS);
+        for(auto& e : ctx->wave_events) if(cudaEventCreate(&e) != cudaSuccess) return -1;
+    }
     for(;;)
     {
         for(int b = 0; b < check_every && rounds < max_rounds; ++b, ++rounds)
         {
             wf_generate_kernel<<<sms * 4, 256, 0, st>>>(sc, job, wb);
+            const bool timed = rounds < WAVE_TIMED_ROUNDS;
+            if(timed) cudaEventRecord(ctx->wave_events[3 * rounds], st);
             if(ctx->bvh == 1) wf_trace_cw_kernel<<<sms * WF_CW_BLOCKS, WF_TRACE_THREADS, 0, st>>>(sc, job, wb);
             else wf_trace_kernel<<<sms * 6, WF_TRACE_THREADS, 0, st>>>(sc, job, wb);
+            if(timed) cudaEventRecord(ctx->wave_events[3 * rounds + 1], st);
             if(ctx->validate && ctx->bvh == 1) wf_validate_kernel<<<sms * 8, 128, 0, st>>>(sc, job, wb, wb.stats);
             wf_phase_kernel<<<1, 32, 0, st>>>(wb, 1, nullptr);
             wf_classify_kernel<<<sms * 8, 256, 0, st>>>(wb);
             wf_shade_kernel<true><<<sms * 8, 128, 0, st>>>(sc, job, wb);
             wf_shade_kernel<false><<<sms * 8, 128, 0, st>>>(sc, job, wb);
+            if(timed) cudaEventRecord(ctx->wave_events[3 * rounds + 2], st);
             wf_phase_kernel<<<1, 32, 0, st>>>(wb, 2, ctx->wave_flag.p);
             launches += 7;
         }
@@ -254,6 +269,18 @@ int launch_wave(ptgpu_ctx* ctx, const Scene& sc, RenderJob job)
         if(*ctx->wave_flag_host == 0u || rounds >= max_rounds) break;
     }
     ctx->last_wave_rounds = rounds;
+    {   // the stream is idle here (flag read-back above)
+        ctx->last_trace_us = ctx->last_shade_us = 0.0;
+        const int nt = rounds < WAVE_TIMED_ROUNDS ? rounds : WAVE_TIMED_ROUNDS;
+        for(int i = 0; i < nt; ++i)
+        {
+            float a = 0.f, b = 0.f;
+            cudaEventElapsedTime(&a, ctx->wave_events[3 * i], ctx->wave_events[3 * i + 1]);
+            cudaEventElapsedTime(&b, ctx->wave_events[3 * i + 1], ctx->wave_events[3 * i + 2]);
+            ctx->last_trace_us += 1e3 * a; ctx->last_shade_us += 1e3 * b;
+        }
+        ctx->last_trace_launches = (uint64_t)nt;
+    }
     if(ctx->validate)
     {
         unsigned long long h = 0;
@@ -425,6 +452,7 @@ void ptgpu_destroy(ptgpu_ctx* ctx)
     ctx->out_bgra.release(); ctx->out_bmp.release(); ctx->out_rgb.release(); ctx->counters.release();
     ctx->mega_state.release(); ctx->wave_mem.release(); ctx->wave_flag.release();
     if(ctx->wave_flag_host) cudaFreeHost(ctx->wave_flag_host);
+    for(auto& e : ctx->wave_events) cudaEventDestroy(e);
     ctx->scratch_a.release(); ctx->scratch_b.release(); ctx->scratch_c.release();
     if(ctx->pinned) cudaFreeHost(ctx->pinned);
     cudaEventDestroy(ctx->ev_begin); cudaEventDestroy(ctx->ev_end);
@@ -896,6 +924,9 @@ int ptgpu_get_stat(ptgpu_ctx* ctx, const char* key, uint64_t* out)
     if(!strcmp(key, "wave_rounds")) { *out = (uint64_t)ctx->last_wave_rounds; return 0; }
     if(!strcmp(key, "wave_lanes")) { *out = ctx->last_wave_lanes; return 0; }
     if(!strcmp(key, "pool_bytes")) { *out = ctx->last_pool_bytes; return 0; }
+    if(!strcmp(key, "trace_us")) { *out = (uint64_t)(ctx->last_trace_us + 0.5); return 0; }
+    if(!strcmp(key, "shade_us")) { *out = (uint64_t)(ctx->last_shade_us + 0.5); return 0; }
+    if(!strcmp(key, "trace_launches")) { *out = ctx->last_trace_launches; return 0; }
     return fail(ctx, "unknown stat '%s'", key);
 }
 
