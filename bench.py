@@ -329,22 +329,23 @@ def main():
             "frame_setup": "ptgpu_set_animation_frame (csrc/frame_setup.cu)" if anim is not None else "snapshot arrays via ptgpu_set_frame",
             "gpu_launches": int(launches),
             "clocks": sampler.result(),
-            "roofline": {"bound": "fp32", "achieved": round(achieved, 3) if achieved else None, "peak": round(peak_tflops, 2),
-                         "unit": "TFLOP/s", "frac": round(achieved / peak_tflops, 4) if achieved else None,
-                         "traffic": prof.get("dram_bytes_per_frame"),
-                         "kernel": {"name": "wf_trace_cw_kernel", "launches": int(trace_launches),
-                                    "avg_launch_ms": round(trace_us / trace_launches / 1e3, 3) if k_ok else None,
-                                    "share_of_device_time": round(trace_us / 1e3 / dev_ms, 4) if k_ok and dev_ms > 0 else None,
-                                    "flops_per_launch": round(trace_flops / trace_launches, 0) if k_ok else None,
-                                    "achieved": round(k_achieved, 3) if k_ok else None,
-                                    "frac": round(k_achieved / peak_tflops, 4) if k_ok else None,
-                                    "traffic": prof.get("wf_trace_cw_dram_bytes_per_launch"),
-                                    "note": "traversal terms of the formula (25 N_node + 56 N_tri + 61 N_blas + 9 N_ray, reference BVH) / "
-                                            "CUDA-event time of the traversal launches on rank 0"},
-                         "note": "whole frame (all kernels; wf_trace is %s of device time): algorithmic flops/path of SURVEY.md 8(d) "
-                                 "from profiles/flops_per_path.json x paths / CUDA-event device time; peak = 148 SM x 128 lanes x 2 x %.0f MHz "
-                                 "(sm_max_mhz of MEASURED_PEAKS.json); tensor cores unused; the path is not HBM-bound" % (
-                                     prof.get("trace_share", "n/a"), sm_max)},
+            # the dominant kernel (wf_trace_cw_kernel), as the contract asks; the whole frame beside it
+            "roofline": {"bound": "fp32", "kernel": "wf_trace_cw_kernel",
+                         "achieved": round(k_achieved, 3) if k_ok else None, "peak": round(peak_tflops, 2),
+                         "unit": "TFLOP/s", "frac": round(k_achieved / peak_tflops, 4) if k_ok else None,
+                         "traffic": prof.get("wf_trace_cw_dram_bytes_per_launch"),
+                         "launches": int(trace_launches),
+                         "avg_launch_ms": round(trace_us / trace_launches / 1e3, 3) if k_ok else None,
+                         "flops_per_launch": round(trace_flops / trace_launches, 0) if k_ok else None,
+                         "share_of_device_time": round(trace_us / 1e3 / dev_ms, 4) if k_ok and dev_ms > 0 else None,
+                         "whole_frame": {"achieved": round(achieved, 3) if achieved else None,
+                                         "frac": round(achieved / peak_tflops, 4) if achieved else None,
+                                         "flops": "all terms of the formula x paths / CUDA-event device time of the frames (all kernels)"},
+                         "note": "FP32-issue roofline (SURVEY.md 8(d)): algorithmic flops counted on the REFERENCE's BVH "
+                                 "(profiles/flops_per_path.json); kernel line = traversal terms 25 N_node + 56 N_tri + 61 N_blas + 9 N_ray "
+                                 "/ CUDA-event time of the traversal launches (render stream, rank 0); peak = 148 SM x 128 lanes x 2 x %.0f MHz "
+                                 "(sm_max_mhz of MEASURED_PEAKS.json); traffic = dram read+write bytes per launch from the ncu --set full capture "
+                                 "(profiles/roofline_inputs.json); tensor cores unused; the path is not HBM-bound" % sm_max},
         }
         if not args.no_cpu_baseline:
             try:

@@ -112,6 +112,7 @@ struct ptgpu_ctx
     std::vector<cudaEvent_t> wave_events;
     double last_trace_us = 0.0, last_shade_us = 0.0;
     uint64_t last_trace_launches = 0;
+    int wave_timed_rounds = 0;
     unsigned long long last_validate_mismatches = 0;
     uint32_t bmp_pitch = 0;
     bool bmp_header_done = false;
@@ -188,6 +189,23 @@ int check_ready(ptgpu_ctx* ctx)
 
 // Carves the wavefront pool out of one allocation and runs rounds of generate / trace / shade until
 // no slot has a ray or a sample left. Returns kernels launched, or -1.
+// Sums the per-round events of the last wavefront frame (waits for the frame).
+void wave_timing(ptgpu_ctx* ctx)
+{
+    if(ctx->wave_timed_rounds <= 0) return;
+    cudaEventSynchronize(ctx->wave_events[3 * (ctx->wave_timed_rounds - 1) + 2]);
+    ctx->last_trace_us = ctx->last_shade_us = 0.0;
+    for(int i = 0; i < ctx->wave_timed_rounds; ++i)
+    {
+        float a = 0.f, b = 0.f;
+        cudaEventElapsedTime(&a, ctx->wave_events[3 * i], ctx->wave_events[3 * i + 1]);
+        cudaEventElapsedTime(&b, ctx->wave_events[3 * i + 1], ctx->wave_events[3 * i + 2]);
+        ctx->last_trace_us += 1e3 * a; ctx->last_shade_us += 1e3 * b;
+    }
+    ctx->last_trace_launches = (uint64_t)ctx->wave_timed_rounds;
+    ctx->wave_timed_rounds = 0;
+}
+
 int launch_wave(ptgpu_ctx* ctx, const Scene& sc, RenderJob job)
 {
     const int tiles_x = (job.w + WF_TILE - 1) / WF_TILE, tiles_y = (job.h + WF_TILE - 1) / WF_TILE;
@@ -264,23 +282,15 @@ int launch_wave(ptgpu_ctx* ctx, const Scene& sc, RenderJob job)
             wf_phase_kernel<<<1, 32, 0, st>>>(wb, 2, ctx->wave_flag.p);
             launches += 7;
         }
+        // every possible round is in flight: no need to ask the device whether paths are left, and the
+        // call stays asynchronous (the shipped 256-spp config: one sample per slot, bounces + 3 rounds)
+        if(rounds >= max_rounds && !ctx->validate) break;
         if(cudaMemcpyAsync(ctx->wave_flag_host, ctx->wave_flag.p, 4, cudaMemcpyDeviceToHost, st) != cudaSuccess) return -1;
         if(cudaStreamSynchronize(st) != cudaSuccess) return -1;
         if(*ctx->wave_flag_host == 0u || rounds >= max_rounds) break;
     }
     ctx->last_wave_rounds = rounds;
-    {   // the stream is idle here (flag read-back above)
-        ctx->last_trace_us = ctx->last_shade_us = 0.0;
-        const int nt = rounds < WAVE_TIMED_ROUNDS ? rounds : WAVE_TIMED_ROUNDS;
-        for(int i = 0; i < nt; ++i)
-        {
-            float a = 0.f, b = 0.f;
-            cudaEventElapsedTime(&a, ctx->wave_events[3 * i], ctx->wave_events[3 * i + 1]);
-            cudaEventElapsedTime(&b, ctx->wave_events[3 * i + 1], ctx->wave_events[3 * i + 2]);
-            ctx->last_trace_us += 1e3 * a; ctx->last_shade_us += 1e3 * b;
-        }
-        ctx->last_trace_launches = (uint64_t)nt;
-    }
+    ctx->wave_timed_rounds = rounds < WAVE_TIMED_ROUNDS ? rounds : WAVE_TIMED_ROUNDS;   // read back lazily by wave_timing()
     if(ctx->validate)
     {
         unsigned long long h = 0;
@@ -924,9 +934,9 @@ int ptgpu_get_stat(ptgpu_ctx* ctx, const char* key, uint64_t* out)
     if(!strcmp(key, "wave_rounds")) { *out = (uint64_t)ctx->last_wave_rounds; return 0; }
     if(!strcmp(key, "wave_lanes")) { *out = ctx->last_wave_lanes; return 0; }
     if(!strcmp(key, "pool_bytes")) { *out = ctx->last_pool_bytes; return 0; }
-    if(!strcmp(key, "trace_us")) { *out = (uint64_t)(ctx->last_trace_us + 0.5); return 0; }
-    if(!strcmp(key, "shade_us")) { *out = (uint64_t)(ctx->last_shade_us + 0.5); return 0; }
-    if(!strcmp(key, "trace_launches")) { *out = ctx->last_trace_launches; return 0; }
+    if(!strcmp(key, "trace_us")) { wave_timing(ctx); *out = (uint64_t)(ctx->last_trace_us + 0.5); return 0; }
+    if(!strcmp(key, "shade_us")) { wave_timing(ctx); *out = (uint64_t)(ctx->last_shade_us + 0.5); return 0; }
+    if(!strcmp(key, "trace_launches")) { wave_timing(ctx); *out = ctx->last_trace_launches; return 0; }
     return fail(ctx, "unknown stat '%s'", key);
 }
 

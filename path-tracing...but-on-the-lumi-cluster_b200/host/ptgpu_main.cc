@@ -1,14 +1,21 @@
 // ptgpu_main.cc — multi-GPU replacement of the reference's main.cc:60-108.
 //
 // Same outputs (output/frame_NNNN.bmp, timing prints), but baseline_render is replaced by the C ABI
-// of libptgpu.so and whole animation frames are sharded over the GPUs of one box: one host thread
-// per GPU, a shared atomic frame counter (frame cost varies ~7x over the animation, so the queue is
-// dynamic, not blocked), no inter-GPU traffic; only the finished 8-bit BMP image returns to the host.
+// of libptgpu.so and whole animation frames are sharded over the GPUs of one box: a shared atomic
+// frame counter (frame cost varies ~7x over the animation, so the queue is dynamic, not blocked), no
+// inter-GPU traffic; only the finished 8-bit BMP image returns to the host.
+//
+// Per GPU the three stages of main.cc's loop body run as a pipeline:
+//     setup thread   setup_animation_frame(frame k+1)      host, 75 ms per frame on one core
+//     render thread  upload + render frame k               device, 70-400 ms
+//     writer thread  fwrite(frame k-1)                     host
+// so the serial host work of the reference loop (scene.cc:271 + bmp.cc:54) hides behind the render.
+// `--serial` keeps the reference's order (setup, render, write, one after the other) for comparison.
 //
 // This file is compiled TOGETHER with the reference's own scene.cc/bvh.cc/mesh.cc (it includes
 // scene.hh / config.hh from the reference tree, -I$REF) — it is the integration a maintainer of
 // the reference would build, see INTEGRATION.md. setup_animation_frame() mutates its `scene`
-// (scene.cc:274-277), so every worker owns a copy of the loaded scene.
+// (scene.cc:274-277), so every worker owns its copies of the loaded scene.
 #include "scene.hh"
 #include "config.hh"
 #include "ptgpu_render.hh"
@@ -16,8 +23,11 @@
 #include <atomic>
 #include <chrono>
 #include <clocale>
+#include <condition_variable>
 #include <cstdio>
 #include <cstring>
+#include <deque>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -27,13 +37,44 @@ static double now_s()
     return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
+// Bounded hand-over between two pipeline stages: indices into a ring of buffers owned by the worker.
+class slot_queue
+{
+public:
+    void push(int v) { { std::lock_guard<std::mutex> l(m_); q_.push_back(v); } cv_.notify_one(); }
+    int pop() // blocks; -1 = closed and drained
+    {
+        std::unique_lock<std::mutex> l(m_);
+        cv_.wait(l, [&] { return !q_.empty() || closed_; });
+        if(q_.empty()) return -1;
+        int v = q_.front(); q_.pop_front();
+        return v;
+    }
+    void close() { { std::lock_guard<std::mutex> l(m_); closed_ = true; } cv_.notify_all(); }
+private:
+    std::mutex m_;
+    std::condition_variable cv_;
+    std::deque<int> q_;
+    bool closed_ = false;
+};
+
+static void write_file(const std::string& out_dir, uint frame, const std::vector<uint8_t>& bmp)
+{
+    char name[512];
+    snprintf(name, sizeof(name), "%s/frame_%04u.bmp", out_dir.c_str(), frame); // main.cc:93-101
+    FILE* f = fopen(name, "w");
+    if(!f) { fprintf(stderr, "Failed to write %s\n", name); exit(1); }
+    fwrite(bmp.data(), 1, bmp.size(), f);
+    fclose(f);
+}
+
 int main(int argc, char** argv)
 {
     setlocale(LC_ALL, "C"); // main.cc:63
     int gpus = 1;
     uint frame_begin = 0, frame_end = 0, frame_step = 1;
     std::string out_dir = "output";
-    bool write_files = true;
+    bool write_files = true, serial = false;
     for(int i = 1; i < argc; ++i)
     {
         if(!strcmp(argv[i], "--gpus") && i + 1 < argc) gpus = atoi(argv[++i]);
@@ -41,7 +82,8 @@ int main(int argc, char** argv)
         else if(!strcmp(argv[i], "--step") && i + 1 < argc) frame_step = atoi(argv[++i]);
         else if(!strcmp(argv[i], "--out") && i + 1 < argc) out_dir = argv[++i];
         else if(!strcmp(argv[i], "--no-write")) write_files = false;
-        else { fprintf(stderr, "usage: %s [--gpus N] [--frames BEGIN END] [--step S] [--out DIR] [--no-write]\n", argv[0]); return 2; }
+        else if(!strcmp(argv[i], "--serial")) serial = true;
+        else { fprintf(stderr, "usage: %s [--gpus N] [--frames BEGIN END] [--step S] [--out DIR] [--no-write] [--serial]\n", argv[0]); return 2; }
     }
 
     double t0 = now_s();
@@ -56,31 +98,83 @@ int main(int argc, char** argv)
 
     std::atomic<uint> next_frame{frame_begin};
     std::atomic<uint> frames_done{0};
+    std::atomic<long long> us_setup{0}, us_render{0}, us_write{0}; // busy time per stage, summed over workers
+    auto timed = [](std::atomic<long long>& acc, auto&& fn) {
+        const double a = now_s();
+        fn();
+        acc += (long long)(1e6 * (now_s() - a));
+    };
     double render_t0 = now_s();
     std::vector<std::thread> workers;
     for(int g = 0; g < gpus; ++g)
     {
+        if(serial)
+        {
+            workers.emplace_back([&, g]() {
+                scene s = loaded; // private copy: setup_animation_frame is not re-entrant
+                ptgpu_detail::renderer<scene> r(g, cfg);
+                std::vector<uint8_t> bmp(r.bmp_size());
+                for(;;)
+                {
+                    uint frame = next_frame.fetch_add(frame_step);
+                    if(frame >= frame_end) break;
+                    timed(us_setup, [&] { setup_animation_frame(s, frame); });
+                    timed(us_render, [&] { r.render_bmp(s, bmp.data()); });
+                    if(write_files) timed(us_write, [&] { write_file(out_dir, frame, bmp); });
+                    frames_done++;
+                }
+            });
+            continue;
+        }
         workers.emplace_back([&, g]() {
-            scene s = loaded; // private copy: setup_animation_frame is not re-entrant
+            // rings: 2 scene copies between setup and render, 3 images between render and writer
+            constexpr int N_SCENES = 2, N_IMAGES = 3;
+            std::vector<scene> scenes(N_SCENES, loaded);
+            uint scene_frame[N_SCENES] = {};
             ptgpu_detail::renderer<scene> r(g, cfg);
-            std::vector<uint8_t> bmp(r.bmp_size());
+            std::vector<std::vector<uint8_t>> images(N_IMAGES, std::vector<uint8_t>(r.bmp_size()));
+            uint image_frame[N_IMAGES] = {};
+            slot_queue scenes_free, scenes_ready, images_free, images_ready;
+            for(int i = 0; i < N_SCENES; ++i) scenes_free.push(i);
+            for(int i = 0; i < N_IMAGES; ++i) images_free.push(i);
+
+            std::thread setup([&]() {
+                for(;;)
+                {
+                    int si = scenes_free.pop();
+                    if(si < 0) break;
+                    uint frame = next_frame.fetch_add(frame_step);
+                    if(frame >= frame_end) break;
+                    timed(us_setup, [&] { setup_animation_frame(scenes[si], frame); });
+                    scene_frame[si] = frame;
+                    scenes_ready.push(si);
+                }
+                scenes_ready.close();
+            });
+            std::thread writer([&]() {
+                for(;;)
+                {
+                    int ii = images_ready.pop();
+                    if(ii < 0) break;
+                    if(write_files) timed(us_write, [&] { write_file(out_dir, image_frame[ii], images[ii]); });
+                    frames_done++;
+                    images_free.push(ii);
+                }
+            });
             for(;;)
             {
-                uint frame = next_frame.fetch_add(frame_step);
-                if(frame >= frame_end) break;
-                setup_animation_frame(s, frame);
-                r.render_bmp(s, bmp.data());
-                if(write_files)
-                {
-                    char name[512];
-                    snprintf(name, sizeof(name), "%s/frame_%04u.bmp", out_dir.c_str(), frame); // main.cc:93-101
-                    FILE* f = fopen(name, "w");
-                    if(!f) { fprintf(stderr, "Failed to write %s\n", name); exit(1); }
-                    fwrite(bmp.data(), 1, bmp.size(), f);
-                    fclose(f);
-                }
-                frames_done++;
+                int si = scenes_ready.pop();
+                if(si < 0) break;
+                int ii = images_free.pop();
+                timed(us_render, [&] { r.render_bmp(scenes[si], images[ii].data()); });
+                image_frame[ii] = scene_frame[si];
+                scenes_free.push(si);
+                images_ready.push(ii);
             }
+            scenes_free.close();
+            images_ready.close();
+            setup.join();
+            writer.join();
         });
     }
     for(auto& w : workers) w.join();
@@ -88,5 +182,7 @@ int main(int argc, char** argv)
     uint n = frames_done.load();
     printf("\n\nRENDERED %u FRAMES ON %d GPU(S) IN %.3fs (%.1f Mpaths/s); TOTAL %.0fms\n", n, gpus, dt,
            n * (double)IMAGE_WIDTH * IMAGE_HEIGHT * SAMPLES_PER_PIXEL / dt / 1e6, 1e3 * (now_s() - t0));
+    printf("STAGE BUSY TIME (all workers): setup_animation_frame %.3fs, upload+render+readback %.3fs, write %.3fs; %s\n",
+           1e-6 * us_setup.load(), 1e-6 * us_render.load(), 1e-6 * us_write.load(), serial ? "serial" : "pipelined");
     return 0;
 }
