@@ -597,6 +597,35 @@ void instance_world_box(const ptgpu_tlas_instance& inst, const float lo[3], cons
     }
 }
 
+// Grows [lo, hi] by the eight corners of an object-space box taken through the instance transform.
+void grow_by_transformed_box(const ptgpu_tlas_instance& inst, const float blo[3], const float bhi[3], float lo[3], float hi[3])
+{
+    const ptgpu_float4* c = inst.transform.r;
+    for(int a = 0; a < 8; ++a)
+    {
+        const float x = (a & 1) ? bhi[0] : blo[0], y = (a & 2) ? bhi[1] : blo[1], z = (a & 4) ? bhi[2] : blo[2];
+        const float v[3] = {
+            c[0].x * x + c[1].x * y + c[2].x * z + c[3].x,
+            c[0].y * x + c[1].y * y + c[2].y * z + c[3].y,
+            c[0].z * x + c[1].z * y + c[2].z * z + c[3].z};
+        for(int k = 0; k < 3; ++k) { lo[k] = std::min(lo[k], v[k]); hi[k] = std::max(hi[k], v[k]); }
+    }
+}
+
+// The traversal tests triangles in object space, these boxes in world space: keep a margin of a few
+// ulps of the coordinates between the two.
+void pad_world_box(float lo[3], float hi[3])
+{
+    float extent = 0.0f, mag = 0.0f;
+    for(int k = 0; k < 3; ++k)
+    {
+        extent = std::max(extent, hi[k] - lo[k]);
+        mag = std::max(mag, std::max(std::fabs(lo[k]), std::fabs(hi[k])));
+    }
+    const float pad = 1e-5f * extent + 1e-6f * mag;
+    for(int k = 0; k < 3; ++k) { lo[k] -= pad; hi[k] += pad; }
+}
+
 } // namespace
 
 bool make_wide_instance(const WideScene& ws, const ptgpu_tlas_instance& inst, uint32_t ref_index, WideInstance& out)
@@ -616,7 +645,13 @@ bool make_wide_instance(const WideScene& ws, const ptgpu_tlas_instance& inst, ui
     out.inv2 = make_float4(r[0].z, r[1].z, r[2].z, r[3].z);
     const WideBlas& wb = ws.blas[found];
     float lo[3] = {wb.lo.x, wb.lo.y, wb.lo.z}, hi[3] = {wb.hi.x, wb.hi.y, wb.hi.z}, wlo[3], whi[3];
-    instance_world_box(inst, lo, hi, wlo, whi);
+    if(bi.sub_boxes.empty()) instance_world_box(inst, lo, hi, wlo, whi);
+    else
+    {
+        for(int k = 0; k < 3; ++k) { wlo[k] = FLT_MAX; whi[k] = -FLT_MAX; }
+        for(const WideSubBox& sb : bi.sub_boxes) grow_by_transformed_box(inst, sb.lo, sb.hi, wlo, whi);
+        pad_world_box(wlo, whi);
+    }
     out.lo = make_float4(wlo[0], wlo[1], wlo[2], 0.0f);
     out.hi = make_float4(whi[0], whi[1], whi[2], 0.0f);
     out.blas = (uint32_t)found;
@@ -705,7 +740,23 @@ bool build_wide_scene(
         wb.lo = make_float4(tree[0].box.lo[0], tree[0].box.lo[1], tree[0].box.lo[2], 0.0f);
         wb.hi = make_float4(tree[0].box.hi[0], tree[0].box.hi[1], tree[0].box.hi[2], 0.0f);
         out.blas.push_back(wb);
-        out.blas_info.push_back(WideBlasInfo{(uint32_t)off, count, m, stack});
+        WideBlasInfo info{(uint32_t)off, count, m, stack, {}};
+        {   // frontier of the source tree six levels below the root
+            std::vector<std::pair<uint32_t, int>> todo{{0u, 0}};
+            while(!todo.empty())
+            {
+                const auto [ni, depth] = todo.back(); todo.pop_back();
+                const TNode& t = tree[ni];
+                if(t.count == 0 || depth == 6)
+                {
+                    WideSubBox sb;
+                    for(int k = 0; k < 3; ++k) { sb.lo[k] = t.box.lo[k]; sb.hi[k] = t.box.hi[k]; }
+                    info.sub_boxes.push_back(sb);
+                }
+                else for(uint32_t c = 0; c < t.count; ++c) todo.push_back({t.first + c, depth + 1});
+            }
+        }
+        out.blas_info.push_back(std::move(info));
         out.max_stack = std::max(out.max_stack, stack);
         off += count;
         index_cursor += 3 * (size_t)tri_count;
@@ -726,6 +777,30 @@ bool build_wide_scene(
             err = "static instance " + std::to_string(i) + " does not match any recovered BLAS/mesh";
             return false;
         }
+    // Static instances get the exact world bounds of their transformed vertices (one pass at upload):
+    // the reference bounds an instance by the transformed corners of its root box (bvh.cc:262-278),
+    // which for a tree turned about its trunk is up to twice the footprint, and 28-36 % of all instance
+    // entries of a frame met no child box of the BLAS root.
+    for(size_t i = 0; i < n_static; ++i)
+    {
+        const ptgpu_tlas_instance& inst = instances[i];
+        const ptgpu_float4* c = inst.transform.r;
+        float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+        const ptgpu_mesh& dm = out.blas_info[out.instances[i].blas].mesh;   // derived from the indices, checked above
+        const ptgpu_float3* v = pos + dm.base_vertex_offset;
+        for(uint32_t k = 0; k < dm.vertex_count; ++k)
+        {
+            const float w[3] = {
+                c[0].x * v[k].x + c[1].x * v[k].y + c[2].x * v[k].z + c[3].x,
+                c[0].y * v[k].x + c[1].y * v[k].y + c[2].y * v[k].z + c[3].y,
+                c[0].z * v[k].x + c[1].z * v[k].y + c[2].z * v[k].z + c[3].z};
+            for(int a = 0; a < 3; ++a) { lo[a] = std::min(lo[a], w[a]); hi[a] = std::max(hi[a], w[a]); }
+        }
+        if(dm.vertex_count == 0) continue;
+        pad_world_box(lo, hi);
+        out.instances[i].lo = make_float4(lo[0], lo[1], lo[2], 0.0f);
+        out.instances[i].hi = make_float4(hi[0], hi[1], hi[2], 0.0f);
+    }
 
     // 3. static TLAS, built once: a subframe's TLAS in the reference differs only by a handful of
     //    dynamic instances (scene.cc:666-674), which the kernels test separately

@@ -10,11 +10,16 @@
 
 namespace pt {
 
+struct WideSubBox { float lo[3], hi[3]; };
+
 struct WideBlasInfo
 {
     uint32_t ref_node_offset, ref_node_count;   // the reference bvh handle this was built from
     ptgpu_mesh mesh;                            // derived; checked against every instance using it
     uint32_t max_stack;                         // stack entries a traversal of this BLAS can need
+    // object-space boxes of the subtrees six levels down (<= 64): the world box of a per-frame instance
+    // is the union of THEIR transformed corners, much tighter under rotation than the transformed root box
+    std::vector<WideSubBox> sub_boxes;
 };
 
 struct WideScene

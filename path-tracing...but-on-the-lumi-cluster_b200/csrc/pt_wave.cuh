@@ -471,7 +471,13 @@ wf_trace_cw_kernel(Scene sc, RenderJob job, WaveBuffers wb)
         auto wants_tri = [&]() { return active && np > 0; };
         auto wants_enter = [&]() { return active && !st.in_blas && st.tgroup.y != 0u; };
         auto node_step = [&]() {
+#ifdef WF_STATS
+            const bool at_root = st.in_blas && st.ngroup.y == 0x80000000u;
+#endif
             cw_node_phase(sc, st, stack);
+#ifdef WF_STATS
+            if(at_root) { atomicAdd(&wb.stats[7], 1ull); if(st.ngroup.y <= 0x00FFFFFFu && st.tgroup.y == 0u) atomicAdd(&wb.stats[16], 1ull); }
+#endif
             if(st.tgroup.y != 0u)
             {
                 if(st.in_blas) { pend[(np++) * WF_TRACE_THREADS] = st.tgroup; st.tgroup.y = 0u; }              // triangles wait for the TRI block
