@@ -443,6 +443,136 @@ struct CollapserW
     }
 };
 
+// Cost-optimal collapse for single-primitive leaves (the dynamic program of Ylitie, Karras and Laine,
+// "Efficient incoherent ray traversal on GPUs through compressed wide BVHs", section 4.1). Every wide
+// node costs its surface area (one eight-child box test per visit, whatever its fill) and the leaves
+// are a given, so the program minimises the summed area of the wide nodes:
+//     C(n, 1)      = A(n) + D(n, 8)                          n becomes a wide node
+//     C(n, i > 1)  = min(D(n, i), C(n, i - 1))               n's subtree as a forest of at most i roots
+//     D(n, j)      = min over 0 < k < j of C(left, k) + C(right, j - k)
+// The greedy "open the largest child while there is room" rule it replaces filled 4.85 of 8 slots.
+struct OptimalCollapser
+{
+    static constexpr int W = CW_WIDTH;
+    struct BNode { Box box; int32_t left = -1, right = -1; uint32_t payload = 0; };
+    std::vector<BNode> b;           // strictly binary copy of the source tree
+    std::vector<float> cost;        // (W - 1) per node: C(n, 1..7)
+    std::vector<uint8_t> split;     // W per node: best k of D(n, 2..8) at [j - 1]
+    std::vector<W8Node>& out;
+
+    explicit OptimalCollapser(std::vector<W8Node>& o) : out(o) {}
+
+    // children [lo, hi) of a source node with more than two children become a balanced binary subtree
+    int32_t binarise_range(const std::vector<TNode>& tree, const std::vector<int32_t>& kids, size_t lo, size_t hi)
+    {
+        if(hi - lo == 1) return kids[lo];
+        const int32_t self = (int32_t)b.size();
+        b.emplace_back();
+        const size_t mid = (lo + hi) / 2;
+        const int32_t l = binarise_range(tree, kids, lo, mid), r = binarise_range(tree, kids, mid, hi);
+        b[self].left = l; b[self].right = r;
+        b[self].box = b[l].box; b[self].box.grow(b[r].box);
+        return self;
+    }
+    int32_t import(const std::vector<TNode>& tree, uint32_t src)
+    {
+        const TNode& t = tree[src];
+        const int32_t self = (int32_t)b.size();
+        b.emplace_back();
+        b[self].box = t.box;
+        if(t.count == 0) { b[self].payload = t.payload; return self; }
+        std::vector<int32_t> kids;
+        for(uint32_t k = 0; k < t.count; ++k) kids.push_back(import(tree, t.first + k));
+        if(kids.size() == 1)
+        {   // a chain link: keep the child, under the parent's box
+            const Box box = b[self].box;
+            b[self] = b[kids[0]];
+            b[self].box = box;
+            return self;
+        }
+        const size_t mid = kids.size() / 2;
+        const int32_t l = binarise_range(tree, kids, 0, mid), r = binarise_range(tree, kids, mid, kids.size());
+        b[self].left = l; b[self].right = r;
+        return self;
+    }
+    bool leaf(int32_t n) const { return b[n].left < 0; }
+    float C(int32_t n, int i) const { return leaf(n) ? 0.0f : cost[(size_t)n * (W - 1) + (i - 1)]; }
+
+    void solve(int32_t n)
+    {   // post-order without recursion on the call stack of deep trees
+        std::vector<std::pair<int32_t, bool>> todo{{n, false}};
+        while(!todo.empty())
+        {
+            auto [v, done] = todo.back(); todo.pop_back();
+            if(leaf(v)) continue;
+            if(!done)
+            {
+                todo.push_back({v, true});
+                todo.push_back({b[v].left, false});
+                todo.push_back({b[v].right, false});
+                continue;
+            }
+            const int32_t l = b[v].left, r = b[v].right;
+            float D[W + 1];
+            for(int j = 2; j <= W; ++j)
+            {
+                float best = FLT_MAX; int best_k = 1;
+                for(int k = 1; k < j; ++k)
+                {
+                    const float c = C(l, std::min(k, W - 1)) + C(r, std::min(j - k, W - 1));
+                    if(c < best) { best = c; best_k = k; }
+                }
+                D[j] = best;
+                split[(size_t)v * W + (j - 1)] = (uint8_t)best_k;
+            }
+            float* c = &cost[(size_t)v * (W - 1)];
+            c[0] = b[v].box.area() + D[W];
+            for(int i = 2; i <= W - 1; ++i) c[i - 1] = std::min(D[i], c[i - 2]);
+        }
+    }
+    // the roots of n's subtree as a forest of at most j trees
+    void collect(int32_t n, int j, std::vector<int32_t>& roots) const
+    {
+        if(leaf(n) || j == 1) { roots.push_back(n); return; }
+        if(j <= W - 1 && C(n, j) == C(n, j - 1) ) { collect(n, j - 1, roots); return; }
+        const int k = split[(size_t)n * W + (j - 1)];
+        collect(b[n].left, std::min(k, W - 1), roots);
+        collect(b[n].right, std::min(j - k, W - 1), roots);
+    }
+    int emit(int32_t n)
+    {
+        const int self = (int)out.size();
+        out.emplace_back();
+        out[self].box = b[n].box;
+        std::vector<int32_t> roots;
+        if(leaf(n)) roots.push_back(n);
+        else
+        {   // n is a wide node: its eight slots go to the two subtrees as D(n, 8) decided
+            const int k = split[(size_t)n * W + (W - 1)];
+            collect(b[n].left, std::min(k, W - 1), roots);
+            collect(b[n].right, std::min(W - k, W - 1), roots);
+        }
+        std::vector<W8Child> ch;
+        for(int32_t r : roots)
+        {
+            W8Child c; c.box = b[r].box;
+            if(leaf(r)) c.leaves.push_back(b[r].payload); else c.inner = emit(r);
+            ch.push_back(std::move(c));
+        }
+        out[self].ch = std::move(ch);
+        return self;
+    }
+    int build(const std::vector<TNode>& tree)
+    {
+        b.reserve(2 * tree.size());
+        const int32_t root = import(tree, 0);
+        cost.assign(b.size() * (W - 1), 0.0f);
+        split.assign(b.size() * W, 1);
+        solve(root);
+        return emit(root);
+    }
+};
+
 inline uint32_t f2u(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
 inline float u2f(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
 
@@ -564,6 +694,11 @@ uint32_t build_cw_tree(const std::vector<TNode>& tree, int leaf_max, std::vector
         std::vector<GItem> items(1);
         items[0].box = tree[0].box; items[0].leaves.push_back(tree[0].payload);
         root = col.from_items(items, tree[0].box);
+    }
+    else if(leaf_max == 1 && CW_OPTIMAL_COLLAPSE)
+    {
+        OptimalCollapser opt(w8);
+        root = opt.build(tree);
     }
     else root = col.build(0);
     CwEmitter em{w8, nodes, emit_leaf};

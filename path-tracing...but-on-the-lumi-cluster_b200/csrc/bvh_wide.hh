@@ -43,6 +43,9 @@ struct WideScene
 
 constexpr int CW_WIDTH = 8;             // children per node
 constexpr int CW_LEAF_MAX = 1;          // triangles per leaf child (the encoding allows 3; measured 1: 245 ms, 2: 251, 3: 255 on frame 520)
+#ifndef CW_OPTIMAL_COLLAPSE
+#define CW_OPTIMAL_COLLAPSE 1        // cost-optimal (dynamic programming) collapse into 8-wide nodes; 0 = greedy
+#endif
 constexpr int CW_STACK = 48;            // traversal stack entries (uint2 each, pt_cwbvh.cuh)
 
 constexpr int WIDE_LEAF_MAX = 4;        // triangles per leaf

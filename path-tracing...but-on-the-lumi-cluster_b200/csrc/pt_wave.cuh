@@ -501,7 +501,11 @@ wf_trace_cw_kernel(Scene sc, RenderJob job, WaveBuffers wb)
             if(st.tgroup.y) stack.set(st.sp++, st.tgroup);
             stack.set(st.sp++, make_uint2(__float_as_uint(st.idir.x), __float_as_uint(st.idir.y)));
             stack.set(st.sp++, make_uint2(__float_as_uint(st.idir.z), (st.oct_inv4 & 0xFFu) | (st.sign_bits << 8)));
-            cw_enter_instance(sc, st, stack, cw_decode_instance(sc, st, st.tgroup.x, bit));
+            const uint32_t inst_id = cw_decode_instance(sc, st, st.tgroup.x, bit);
+#ifdef WF_STATS
+            atomicAdd(&wb.stats[24 + min(sc.winst[inst_id].blas, 15u)], 1ull);
+#endif
+            cw_enter_instance(sc, st, stack, inst_id);
         };
 
         bool progress = false;

@@ -223,7 +223,7 @@ int launch_wave(ptgpu_ctx* ctx, const Scene& sc, RenderJob job)
         o_sd = carve(16ull * n_slots), o_hit = carve(16ull * n_slots), o_prim = carve(4ull * n_slots),
         o_att = carve(16ull * n_slots), o_con = carve(16ull * n_slots), o_nee = carve(16ull * n_slots),
         o_sum = carve(16ull * n_slots), o_cur = carve(8ull * n_slots), o_vis = carve(4ull * n_slots),
-        o_qt = carve(4ull * 3ull * (n_slots + 64)), o_st = carve(n_slots), o_qf = carve(4ull * (n_slots + 64)), o_qn = carve(4ull * (n_slots + 64)), o_cnt = carve(sizeof(WaveCounters)), o_stats = carve(24 * 8);
+        o_qt = carve(4ull * 3ull * (n_slots + 64)), o_st = carve(n_slots), o_qf = carve(4ull * (n_slots + 64)), o_qn = carve(4ull * (n_slots + 64)), o_cnt = carve(sizeof(WaveCounters)), o_stats = carve(40 * 8);
     if(ctx->wave_mem.reserve(off) != cudaSuccess) return -1;
     if(!ctx->wave_flag_host)
     {
@@ -248,7 +248,7 @@ int launch_wave(ptgpu_ctx* ctx, const Scene& sc, RenderJob job)
 
     cudaStream_t st = ctx->stream;
     int launches = 0;
-    cudaMemsetAsync(wb.stats, 0, 24 * 8, st);
+    cudaMemsetAsync(wb.stats, 0, 40 * 8, st);
     wf_init_kernel<<<(n_slots + 255) / 256, 256, 0, st>>>(wb, job); launches++;
     const int sms = ctx->sm_count;
     // worst case: every sample of a slot takes all bounces
@@ -302,13 +302,16 @@ int launch_wave(ptgpu_ctx* ctx, const Scene& sc, RenderJob job)
     ctx->last_pool_bytes = off;
 #ifdef WF_STATS
     {
-        unsigned long long h[24];
+        unsigned long long h[40];
         cudaMemcpyAsync(h, wb.stats, sizeof(h), cudaMemcpyDeviceToHost, st);
         cudaStreamSynchronize(st);
         fprintf(stderr, "WF_STATS node-iters %llu (executed %llu): lanes node %.2f idle %.2f enter-wait %.2f pend-full %.2f tri-wait %.2f | tri steps %llu lanes %.2f | enter steps %llu lanes %.2f | forced %llu (n %.2f t %.2f e %.2f)\n",
                 h[0], h[6], (double)h[1] / h[0], (double)h[2] / h[0], (double)h[3] / h[0], (double)h[4] / h[0], (double)h[5] / h[0],
                 h[8], h[8] ? (double)h[9] / h[8] : 0.0, h[10], h[10] ? (double)h[11] / h[10] : 0.0,
                 h[12], h[12] ? (double)h[13] / h[12] : 0.0, h[12] ? (double)h[14] / h[12] : 0.0, h[12] ? (double)h[15] / h[12] : 0.0);
+        fprintf(stderr, "WF_STATS entries by BLAS:");
+        for(int i = 0; i < 16; ++i) if(h[24 + i]) fprintf(stderr, " [%d] %llu", i, h[24 + i]);
+        fprintf(stderr, "\n");
         fprintf(stderr, "WF_STATS instance root tests %llu, of which no child box hit %llu (%.1f %%)\n", h[7], h[16], h[7] ? 100.0 * h[16] / h[7] : 0.0);
     }
 #endif
