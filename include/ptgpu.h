@@ -113,6 +113,23 @@ int ptgpu_upload_static(
     const ptgpu_float4* albedo, const ptgpu_float4* material, size_t n_verts,
     const ptgpu_tlas_instance* instances, size_t n_static);
 
+/* the static scene from its meshes alone. The reference hands baseline_render BVHs that
+ * build_blas made (bvh.cc:231-260: full-sweep SAH, eight link tables per BVH, 2.6 s of load_scene);
+ * this entry point needs none of them: every BLAS is built here from the triangles of `meshes`
+ * (binned SAH above 256 primitives, full sweep below, single-triangle leaves, then the cost-optimal
+ * collapse into compressed 8-wide nodes), and instances name their BLAS by their `m` member
+ * (`blas` is ignored). Afterwards use ptgpu_set_frame_ranges / ptgpu_set_animation_frame for the
+ * per-frame state (ptgpu_set_frame wants the reference's TLAS arrays); "traversal" = 1 and the event
+ * counters, which walk the reference's link tables, are unavailable. `meshes` must list every mesh
+ * that a static or per-frame instance will use. Hits are the same as with ptgpu_upload_static. */
+int ptgpu_upload_meshes(
+    ptgpu_ctx* ctx,
+    const uint32_t* indices, size_t n_indices,
+    const ptgpu_float3* pos, const ptgpu_float3* normal,
+    const ptgpu_float4* albedo, const ptgpu_float4* material, size_t n_verts,
+    const ptgpu_mesh* meshes, size_t n_meshes,
+    const ptgpu_tlas_instance* static_instances, size_t n_static);
+
 /* ---- per frame: everything setup_animation_frame() produces (scene.cc:271-718) -------------- */
 
 /* subframes[n_subframes]         s.subframes (scene.hh:65), one per 8 samples
@@ -193,6 +210,14 @@ int ptgpu_render_async(ptgpu_ctx* ctx);
 int ptgpu_fetch_bgra(ptgpu_ctx* ctx, uint8_t* out_bgra);
 int ptgpu_fetch_bmp(ptgpu_ctx* ctx, uint8_t* out_bmp);
 int ptgpu_sync(ptgpu_ctx* ctx);
+
+/* validator.py:41-52 on the device-resident frame of the last render: the frame is
+ * box-downscaled by 2 (skimage.transform.downscale_local_mean, zero padded), truncated to 8 bits and
+ * compared by PSNR (data range 255) with `ref_rgb_half`, the course's half-size reference image as
+ * ceil(height/2) x ceil(width/2) x 3 bytes, RGB, row 0 = top. *good = 1 when PSNR >= 32 dB
+ * (ACCEPT_MIN_PSNR). Only the half-size reference goes up and one 8-byte sum comes back, so a whole
+ * animation can be validated without reading its frames back or a Python pass over 1800 files. */
+int ptgpu_validate_frame(ptgpu_ctx* ctx, const uint8_t* ref_rgb_half, double* psnr, int32_t* good);
 /* Device time (CUDA events on the context's stream) of the most recent finished render, in ms;
  * `launches` (may be NULL) receives the number of kernels it launched. */
 int ptgpu_last_render_ms(ptgpu_ctx* ctx, float* ms, int32_t* launches);
@@ -281,6 +306,11 @@ int ptgpu_get_stat(ptgpu_ctx* ctx, const char* key, uint64_t* out);
 int ptgpu_host_flatten_check(
     const ptgpu_bvh_node* nodes, size_t n_nodes, const ptgpu_bvh_link* links, size_t n_links,
     const uint32_t* indices, size_t n_indices, const ptgpu_float3* pos, size_t n_verts,
+    const ptgpu_tlas_instance* instances, size_t n_static, uint64_t out[8], char* err, size_t err_len);
+/* The same for ptgpu_upload_meshes' own BLAS builder. */
+int ptgpu_host_build_check(
+    const uint32_t* indices, size_t n_indices, const ptgpu_float3* pos, size_t n_verts,
+    const ptgpu_mesh* meshes, size_t n_meshes,
     const ptgpu_tlas_instance* instances, size_t n_static, uint64_t out[8], char* err, size_t err_len);
 
 #ifdef __cplusplus

@@ -37,6 +37,7 @@ class Animation:
         for i, name in enumerate(MESH_ORDER):
             meshes[i, :4] = data["meshes"][name]["mesh"]
             meshes[i, 4:] = data["meshes"][name]["blas"]
+        self.mesh_rows = [tuple(int(x) for x in meshes[i, :4]) for i in range(len(MESH_ORDER))]   # the per-frame meshes
         self.handle = C.c_void_p()
         rc = self.lib.ptgpu_anim_create(C.byref(self.handle), keys.ctypes.data_as(C.c_void_p), keys.shape[0],
                                         meshes.ctypes.data_as(C.c_void_p), C.byref(self.config))

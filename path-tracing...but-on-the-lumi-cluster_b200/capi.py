@@ -15,7 +15,8 @@ SYMBOLS = [
     "ptgpu_render_rect", "ptgpu_trace_samples", "ptgpu_tonemap", "ptgpu_trace_closest",
     "ptgpu_pcg4d", "ptgpu_render_async", "ptgpu_fetch_bgra", "ptgpu_fetch_bmp", "ptgpu_sync",
     "ptgpu_last_render_ms", "ptgpu_set_option", "ptgpu_read_counters", "ptgpu_scene_stats",
-    "ptgpu_host_flatten_check", "ptgpu_get_stat",
+    "ptgpu_host_flatten_check", "ptgpu_get_stat", "ptgpu_validate_frame",
+    "ptgpu_upload_meshes", "ptgpu_host_build_check",
     "ptgpu_anim_create", "ptgpu_anim_destroy", "ptgpu_anim_subframe_count", "ptgpu_anim_max_instances",
     "ptgpu_anim_frame_count", "ptgpu_anim_frame", "ptgpu_set_animation_frame",
 ]
@@ -109,6 +110,9 @@ def load_library():
     L.ptgpu_set_animation_frame.argtypes = [vp, vp, C.c_uint32]
     L.ptgpu_get_stat.argtypes = [vp, C.c_char_p, C.POINTER(C.c_uint64)]
     L.ptgpu_host_flatten_check.argtypes = [vp, sz, vp, sz, vp, sz, vp, sz, vp, sz, C.POINTER(C.c_uint64), C.c_char_p, sz]
+    L.ptgpu_upload_meshes.argtypes = [vp, vp, sz, vp, vp, vp, vp, sz, vp, sz, vp, sz]
+    L.ptgpu_host_build_check.argtypes = [vp, sz, vp, sz, vp, sz, vp, sz, C.POINTER(C.c_uint64), C.c_char_p, sz]
+    L.ptgpu_validate_frame.argtypes = [vp, vp, C.POINTER(C.c_double), C.POINTER(C.c_int32)]
     for name in SYMBOLS:
         if name not in ("ptgpu_default_config", "ptgpu_destroy", "ptgpu_last_error", "ptgpu_bmp_size", "ptgpu_anim_destroy",
                         "ptgpu_anim_subframe_count", "ptgpu_anim_max_instances", "ptgpu_anim_frame_count"):

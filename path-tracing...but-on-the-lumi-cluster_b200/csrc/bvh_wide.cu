@@ -273,11 +273,15 @@ uint32_t collapse_tree(const std::vector<TNode>& tree, int leaf_max, std::vector
     return c.build(0).second + 1;
 }
 
-// ---- small full-sweep SAH builder for the static TLAS (n ~ 10^3) ----------------------------------
+// ---- SAH builder: the static TLAS (n ~ 10^3, full sweep) and, for ptgpu_upload_meshes, the BLASes --------
 
 struct Prim { Box box; uint32_t id; };
 
-void build_sah(std::vector<Prim>& prims, size_t begin, size_t end, std::vector<TNode>& tree, uint32_t self)
+// Binary SAH tree over `prims`, single-primitive leaves. Ranges of at most `sweep_below` primitives are
+// split by the full sweep (every split position on every axis, as bvh.cc:43-140 does); larger ranges by
+// 32 centroid bins per axis, which costs O(n) per level instead of three sorts.
+void build_sah(std::vector<Prim>& prims, size_t begin, size_t end, std::vector<TNode>& tree, uint32_t self,
+               size_t sweep_below = SIZE_MAX)
 {
     // children are appended contiguously so that [first, first+count) addressing works
     const size_t n = end - begin;
@@ -290,33 +294,109 @@ void build_sah(std::vector<Prim>& prims, size_t begin, size_t end, std::vector<T
         tree[self].payload = prims[begin].id;
         return;
     }
-    float best_cost = FLT_MAX; int best_axis = 0; size_t best_split = begin + n / 2;
-    std::vector<float> right_area(n);
-    for(int axis = 0; axis < 3; ++axis)
+    size_t best_split = begin + n / 2;
+    if(n <= sweep_below)
     {
-        std::sort(prims.begin() + begin, prims.begin() + end, [axis](const Prim& x, const Prim& y) {
-            float cx = x.box.lo[axis] + x.box.hi[axis], cy = y.box.lo[axis] + y.box.hi[axis];
+        float best_cost = FLT_MAX; int best_axis = 0;
+        std::vector<float> right_area(n);
+        for(int axis = 0; axis < 3; ++axis)
+        {
+            std::sort(prims.begin() + begin, prims.begin() + end, [axis](const Prim& x, const Prim& y) {
+                float cx = x.box.lo[axis] + x.box.hi[axis], cy = y.box.lo[axis] + y.box.hi[axis];
+                return cx < cy || (cx == cy && x.id < y.id);
+            });
+            Box acc; acc.reset();
+            for(size_t i = n; i-- > 1;) { acc.grow(prims[begin + i].box); right_area[i] = acc.area(); }
+            acc.reset();
+            for(size_t i = 1; i < n; ++i)
+            {
+                acc.grow(prims[begin + i - 1].box);
+                float cost = acc.area() * (float)i + right_area[i] * (float)(n - i);
+                if(cost < best_cost) { best_cost = cost; best_axis = axis; best_split = begin + i; }
+            }
+        }
+        std::sort(prims.begin() + begin, prims.begin() + end, [best_axis](const Prim& x, const Prim& y) {
+            float cx = x.box.lo[best_axis] + x.box.hi[best_axis], cy = y.box.lo[best_axis] + y.box.hi[best_axis];
             return cx < cy || (cx == cy && x.id < y.id);
         });
-        Box acc; acc.reset();
-        for(size_t i = n; i-- > 1;) { acc.grow(prims[begin + i].box); right_area[i] = acc.area(); }
-        acc.reset();
-        for(size_t i = 1; i < n; ++i)
+    }
+    else
+    {
+        constexpr int BINS = 32;
+        float clo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, chi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+        for(size_t i = begin; i < end; ++i)
+            for(int a = 0; a < 3; ++a)
+            {
+                const float c = prims[i].box.lo[a] + prims[i].box.hi[a];
+                clo[a] = std::min(clo[a], c); chi[a] = std::max(chi[a], c);
+            }
+        float best_cost = FLT_MAX; int best_axis = -1, best_bin = 0;
+        for(int a = 0; a < 3; ++a)
         {
-            acc.grow(prims[begin + i - 1].box);
-            float cost = acc.area() * (float)i + right_area[i] * (float)(n - i);
-            if(cost < best_cost) { best_cost = cost; best_axis = axis; best_split = begin + i; }
+            const float ext = chi[a] - clo[a];
+            if(!(ext > 0.0f)) continue;
+            const float scale = (float)BINS / ext;
+            Box bb[BINS]; uint32_t cnt[BINS] = {};
+            for(int k = 0; k < BINS; ++k) bb[k].reset();
+            for(size_t i = begin; i < end; ++i)
+            {
+                const int k = std::min(BINS - 1, (int)((prims[i].box.lo[a] + prims[i].box.hi[a] - clo[a]) * scale));
+                bb[k].grow(prims[i].box); cnt[k]++;
+            }
+            float right_area[BINS]; uint32_t right_cnt[BINS];
+            Box acc; acc.reset(); uint32_t c = 0;
+            for(int k = BINS - 1; k > 0; --k) { if(cnt[k]) acc.grow(bb[k]); c += cnt[k]; right_area[k] = c ? acc.area() : 0.0f; right_cnt[k] = c; }
+            acc.reset(); c = 0;
+            for(int k = 1; k < BINS; ++k)
+            {
+                if(cnt[k - 1]) acc.grow(bb[k - 1]);
+                c += cnt[k - 1];
+                if(c == 0 || right_cnt[k] == 0) continue;
+                const float cost = acc.area() * (float)c + right_area[k] * (float)right_cnt[k];
+                if(cost < best_cost) { best_cost = cost; best_axis = a; best_bin = k; }
+            }
+        }
+        if(best_axis >= 0)
+        {
+            const int a = best_axis;
+            const float scale = (float)BINS / (chi[a] - clo[a]), lo = clo[a];
+            auto mid = std::partition(prims.begin() + begin, prims.begin() + end, [&](const Prim& x) {
+                return std::min(BINS - 1, (int)((x.box.lo[a] + x.box.hi[a] - lo) * scale)) < best_bin;
+            });
+            best_split = (size_t)(mid - prims.begin());
+        }
+        if(best_axis < 0 || best_split == begin || best_split == end)
+        {   // all centroids coincide: halve the range in primitive order
+            std::sort(prims.begin() + begin, prims.begin() + end, [](const Prim& x, const Prim& y) { return x.id < y.id; });
+            best_split = begin + n / 2;
         }
     }
-    std::sort(prims.begin() + begin, prims.begin() + end, [best_axis](const Prim& x, const Prim& y) {
-        float cx = x.box.lo[best_axis] + x.box.hi[best_axis], cy = y.box.lo[best_axis] + y.box.hi[best_axis];
-        return cx < cy || (cx == cy && x.id < y.id);
-    });
     const uint32_t first = (uint32_t)tree.size();
     tree.emplace_back(); tree.emplace_back();
     tree[self].first = first; tree[self].count = 2;
-    build_sah(prims, begin, best_split, tree, first);
-    build_sah(prims, best_split, end, tree, first + 1);
+    build_sah(prims, begin, best_split, tree, first, sweep_below);
+    build_sah(prims, best_split, end, tree, first + 1, sweep_below);
+}
+
+// the BLAS of one mesh straight from its triangles (no reference bvh arrays).
+void build_mesh_tree(const uint32_t* indices, const ptgpu_float3* pos, const ptgpu_mesh& m, std::vector<TNode>& tree)
+{
+    std::vector<Prim> prims(m.triangle_count);
+    for(uint32_t t = 0; t < m.triangle_count; ++t)
+    {
+        Box b; b.reset();
+        for(int k = 0; k < 3; ++k)
+        {
+            const ptgpu_float3& v = pos[m.base_vertex_offset + indices[m.index_offset + 3 * (size_t)t + k]];
+            const float c[3] = {v.x, v.y, v.z};
+            for(int a = 0; a < 3; ++a) { b.lo[a] = std::min(b.lo[a], c[a]); b.hi[a] = std::max(b.hi[a], c[a]); }
+        }
+        prims[t].box = b; prims[t].id = t;
+    }
+    tree.clear();
+    tree.resize(1);
+    tree.reserve(2 * (size_t)m.triangle_count);
+    build_sah(prims, 0, prims.size(), tree, 0, 256);
 }
 
 // ---- compressed 8-wide BVH (after Ylitie, Karras, Laine 2017) --------------------------------------
@@ -766,11 +846,13 @@ void pad_world_box(float lo[3], float hi[3])
 bool make_wide_instance(const WideScene& ws, const ptgpu_tlas_instance& inst, uint32_t ref_index, WideInstance& out)
 {
     int found = -1;
+    // an instance names its BLAS by the reference bvh handle, or (scene built from meshes) by its mesh
     for(size_t b = 0; b < ws.blas_info.size(); ++b)
-        if(ws.blas_info[b].ref_node_offset == inst.blas.node_offset) { found = (int)b; break; }
+        if(ws.from_meshes ? ws.blas_info[b].mesh.index_offset == inst.m.index_offset
+                          : ws.blas_info[b].ref_node_offset == inst.blas.node_offset) { found = (int)b; break; }
     if(found < 0) return false;
     const WideBlasInfo& bi = ws.blas_info[found];
-    if(bi.ref_node_count != inst.blas.node_count || bi.mesh.index_offset != inst.m.index_offset ||
+    if((!ws.from_meshes && bi.ref_node_count != inst.blas.node_count) || bi.mesh.index_offset != inst.m.index_offset ||
        bi.mesh.base_vertex_offset != inst.m.base_vertex_offset || bi.mesh.triangle_count != inst.m.triangle_count)
         return false;
     const ptgpu_float4* r = inst.inv_transform.r; // columns
@@ -799,30 +881,47 @@ bool build_wide_scene(
     const ptgpu_bvh_node* nodes, size_t n_nodes, const ptgpu_bvh_link* links,
     const uint32_t* indices, size_t n_indices, const ptgpu_float3* pos, size_t n_verts,
     const ptgpu_tlas_instance* instances, size_t n_static,
-    WideScene& out, std::string& err)
+    WideScene& out, std::string& err, const ptgpu_mesh* meshes, size_t n_meshes)
 {
     out = WideScene();
-    // 1. every BVH in the static region, in build order (= mesh load order, scene.cc:42-47)
-    size_t off = 0, index_cursor = 0, vertex_cursor = 0;
+    out.from_meshes = nodes == nullptr;
+    // 1. every BLAS: recovered from the reference's static BVH region, in build order (= mesh load
+    //    order, scene.cc:42-47), or built here from the triangles of each mesh of the table
+    size_t off = 0, index_cursor = 0, vertex_cursor = 0, mesh_i = 0;
     std::vector<TNode> tree;
     uint32_t cw_blas_depth = 0;
-    while(off < n_nodes)
+    while(out.from_meshes ? mesh_i < n_meshes : off < n_nodes)
     {
-        uint32_t count = recover_tree(nodes, links, n_nodes, off, tree, err);
-        if(count == 0) { err = "BVH at node " + std::to_string(off) + ": " + err; return false; }
-        uint32_t tri_count = 0;
-        for(const TNode& t : tree) if(t.count == 0) tri_count++;
-        // the i-th BLAS belongs to the i-th mesh: indices and vertices are appended in load order
-        // (mesh.cc:118-119, 255-259), and every vertex is referenced by at least one index
+        uint32_t count = 0, tri_count = 0;
         ptgpu_mesh m;
-        m.triangle_count = tri_count;
-        m.index_offset = (uint32_t)index_cursor;
-        m.base_vertex_offset = (uint32_t)vertex_cursor;
-        if(index_cursor + 3 * (size_t)tri_count > n_indices) { err = "index buffer shorter than the BLAS leaves imply"; return false; }
-        uint32_t vmax = 0;
-        for(size_t i = 0; i < 3 * (size_t)tri_count; ++i) vmax = std::max(vmax, indices[index_cursor + i]);
-        m.vertex_count = vmax + 1;
-        if(vertex_cursor + m.vertex_count > n_verts) { err = "vertex buffer shorter than the indices imply"; return false; }
+        if(out.from_meshes)
+        {
+            m = meshes[mesh_i++];
+            if(m.triangle_count == 0) { err = "mesh " + std::to_string(mesh_i - 1) + " has no triangles"; return false; }
+            if((size_t)m.index_offset + 3 * (size_t)m.triangle_count > n_indices) { err = "mesh " + std::to_string(mesh_i - 1) + ": indices beyond the index buffer"; return false; }
+            uint32_t vmax = 0;
+            for(size_t i = 0; i < 3 * (size_t)m.triangle_count; ++i) vmax = std::max(vmax, indices[m.index_offset + i]);
+            if((size_t)m.base_vertex_offset + vmax >= n_verts) { err = "mesh " + std::to_string(mesh_i - 1) + ": vertex index beyond the vertex buffer"; return false; }
+            m.vertex_count = vmax + 1;
+            build_mesh_tree(indices, pos, m, tree);
+            tri_count = m.triangle_count;
+        }
+        else
+        {
+            count = recover_tree(nodes, links, n_nodes, off, tree, err);
+            if(count == 0) { err = "BVH at node " + std::to_string(off) + ": " + err; return false; }
+            for(const TNode& t : tree) if(t.count == 0) tri_count++;
+            // the i-th BLAS belongs to the i-th mesh: indices and vertices are appended in load order
+            // (mesh.cc:118-119, 255-259), and every vertex is referenced by at least one index
+            m.triangle_count = tri_count;
+            m.index_offset = (uint32_t)index_cursor;
+            m.base_vertex_offset = (uint32_t)vertex_cursor;
+            if(index_cursor + 3 * (size_t)tri_count > n_indices) { err = "index buffer shorter than the BLAS leaves imply"; return false; }
+            uint32_t vmax = 0;
+            for(size_t i = 0; i < 3 * (size_t)tri_count; ++i) vmax = std::max(vmax, indices[index_cursor + i]);
+            m.vertex_count = vmax + 1;
+            if(vertex_cursor + m.vertex_count > n_verts) { err = "vertex buffer shorter than the indices imply"; return false; }
+        }
 
         WideBlas wb{};
         wb.node_offset = (uint32_t)out.nodes.size();
@@ -897,7 +996,7 @@ bool build_wide_scene(
         index_cursor += 3 * (size_t)tri_count;
         vertex_cursor += m.vertex_count;
     }
-    if(index_cursor != n_indices || vertex_cursor != n_verts)
+    if(!out.from_meshes && (index_cursor != n_indices || vertex_cursor != n_verts))
     {
         err = "mesh buffers do not line up with the BLAS sequence (indices " + std::to_string(index_cursor) + "/" +
             std::to_string(n_indices) + ", vertices " + std::to_string(vertex_cursor) + "/" + std::to_string(n_verts) + ")";

@@ -39,6 +39,7 @@ struct WideScene
     std::vector<uint32_t> cw_blas_root; // per BLAS: root node index
     uint32_t cw_tlas_root = 0;
     uint32_t cw_max_stack = 0;          // group-stack entries a traversal can need
+    bool from_meshes = false;           // BLASes built from triangles (ptgpu_upload_meshes), not recovered
 };
 
 constexpr int CW_WIDTH = 8;             // children per node
@@ -55,7 +56,8 @@ bool build_wide_scene(
     const ptgpu_bvh_node* nodes, size_t n_nodes, const ptgpu_bvh_link* links,
     const uint32_t* indices, size_t n_indices, const ptgpu_float3* pos, size_t n_verts,
     const ptgpu_tlas_instance* instances, size_t n_static,
-    WideScene& out, std::string& err);
+    WideScene& out, std::string& err,
+    const ptgpu_mesh* meshes = nullptr, size_t n_meshes = 0);  // nodes == nullptr: build every BLAS from `meshes`
 
 // Fills the traversal record of one instance (static or per-frame). False if its BLAS is unknown.
 bool make_wide_instance(const WideScene& ws, const ptgpu_tlas_instance& inst, uint32_t ref_index, WideInstance& out);

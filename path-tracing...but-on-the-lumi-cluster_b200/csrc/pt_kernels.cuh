@@ -174,4 +174,34 @@ __global__ void bmp_header_kernel(uint8_t* bmp, uint32_t w, uint32_t h, uint32_t
     put32(0x32, 0);
 }
 
+// validator.py:41-52 on the finished device frame: 2x2 block mean of the own frame (zero padded,
+// skimage.transform.downscale_local_mean), truncated to 8 bits (astype), squared difference against
+// the half-size reference image (RGB, row 0 = top). Integer arithmetic throughout: sum[0] is exact.
+__global__ void validate_psnr_kernel(const uchar4* __restrict__ bgra, uint32_t w, uint32_t h,
+                                     const uint8_t* __restrict__ ref_rgb, uint32_t hw, uint32_t hh,
+                                     unsigned long long* sum)
+{
+    unsigned long long sse = 0;
+    for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < hw * hh; i += gridDim.x * blockDim.x)
+    {
+        const uint32_t x = i % hw, y = i / hw;
+        uint32_t r = 0, g = 0, b = 0;
+        #pragma unroll
+        for(int k = 0; k < 4; ++k)
+        {
+            const uint32_t px = 2 * x + (k & 1), py = 2 * y + (k >> 1);
+            if(px < w && py < h)
+            {
+                const uchar4 p = bgra[(size_t)py * w + px]; // x = blue, y = green, z = red (main.cc:39-43)
+                r += p.z; g += p.y; b += p.x;
+            }
+        }
+        const int dr = (int)(r >> 2) - (int)ref_rgb[3 * (size_t)i], dg = (int)(g >> 2) - (int)ref_rgb[3 * (size_t)i + 1],
+                  db = (int)(b >> 2) - (int)ref_rgb[3 * (size_t)i + 2];
+        sse += (unsigned long long)(dr * dr + dg * dg + db * db);
+    }
+    for(int o = 16; o > 0; o >>= 1) sse += __shfl_down_sync(0xFFFFFFFFu, sse, o);
+    if((threadIdx.x & 31) == 0 && sse) atomicAdd(sum, sse);
+}
+
 } // namespace pt

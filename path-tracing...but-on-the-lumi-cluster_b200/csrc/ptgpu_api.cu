@@ -74,6 +74,7 @@ struct ptgpu_ctx
     DevBuf<RefInstance> instances; // static + dynamic
     size_t n_static_nodes = 0, n_static = 0, n_verts = 0, n_indices = 0;
     bool have_static = false;
+    bool have_ref_bvh = false;      // false after ptgpu_upload_meshes: no reference nodes/links on the device
     std::vector<ptgpu_tlas_instance> host_static; // kept for the wide instance records
 
     // wide layout
@@ -187,8 +188,6 @@ int check_ready(ptgpu_ctx* ctx)
     return 0;
 }
 
-// Carves the wavefront pool out of one allocation and runs rounds of generate / trace / shade until
-// no slot has a ray or a sample left. Returns kernels launched, or -1.
 // Sums the per-round events of the last wavefront frame (waits for the frame).
 void wave_timing(ptgpu_ctx* ctx)
 {
@@ -206,6 +205,8 @@ void wave_timing(ptgpu_ctx* ctx)
     ctx->wave_timed_rounds = 0;
 }
 
+// Carves the wavefront pool out of one allocation and runs rounds of generate / trace / shade until
+// no slot has a ray or a sample left. Returns kernels launched, or -1.
 int launch_wave(ptgpu_ctx* ctx, const Scene& sc, RenderJob job)
 {
     const int tiles_x = (job.w + WF_TILE - 1) / WF_TILE, tiles_y = (job.h + WF_TILE - 1) / WF_TILE;
@@ -479,31 +480,33 @@ const char* ptgpu_last_error(const ptgpu_ctx* ctx)
     return ctx ? ctx->error.c_str() : g_create_error.c_str();
 }
 
-int ptgpu_upload_static(
+// Static scene upload. nodes/links == nullptr: no reference BVH, every BLAS is built from `meshes`.
+static int upload_static_common(
     ptgpu_ctx* ctx,
     const ptgpu_bvh_node* nodes, size_t n_nodes,
     const ptgpu_bvh_link* links, size_t n_links,
     const uint32_t* indices, size_t n_indices,
     const ptgpu_float3* pos, const ptgpu_float3* normal,
     const ptgpu_float4* albedo, const ptgpu_float4* material, size_t n_verts,
-    const ptgpu_tlas_instance* instances, size_t n_static)
+    const ptgpu_tlas_instance* instances, size_t n_static,
+    const ptgpu_mesh* meshes, size_t n_meshes)
 {
-    if(!ctx) return 1;
-    if(!nodes || !links || !indices || !pos || !normal || !albedo || !material || !instances)
-        return fail(ctx, "ptgpu_upload_static: null array");
-    if(n_links != 8 * n_nodes) return fail(ctx, "ptgpu_upload_static: n_links (%zu) must be 8*n_nodes (%zu)", n_links, n_nodes);
-    if(n_static == 0 || n_nodes == 0) return fail(ctx, "ptgpu_upload_static: empty scene");
     if(use(ctx)) return 1;
 
     // reference layout, with head-room after the static region for the per-frame TLAS (links mode)
-    CK(ctx->ref_nodes.reserve(3 * n_nodes));
-    CK(ctx->ref_links.reserve(n_links));
+    CK(ctx->ref_nodes.reserve(3 * n_nodes + 16));
+    CK(ctx->ref_links.reserve(n_links + 16));
     CK(ctx->indices.reserve(n_indices));
     CK(ctx->pos.reserve(n_verts)); CK(ctx->normal.reserve(n_verts));
     CK(ctx->albedo.reserve(n_verts)); CK(ctx->material.reserve(n_verts));
     CK(ctx->instances.reserve(n_static + 64));
-    CK(cudaMemcpy(ctx->ref_nodes.p, nodes, n_nodes * sizeof(ptgpu_bvh_node), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(ctx->ref_links.p, links, n_links * sizeof(ptgpu_bvh_link), cudaMemcpyHostToDevice));
+    if(nodes)
+    {
+        CK(cudaMemcpy(ctx->ref_nodes.p, nodes, n_nodes * sizeof(ptgpu_bvh_node), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(ctx->ref_links.p, links, n_links * sizeof(ptgpu_bvh_link), cudaMemcpyHostToDevice));
+    }
+    ctx->have_ref_bvh = nodes != nullptr;
+    if(!ctx->have_ref_bvh) ctx->traversal = 0;
     CK(cudaMemcpy(ctx->indices.p, indices, n_indices * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(ctx->pos.p, pos, n_verts * 16, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(ctx->normal.p, normal, n_verts * 16, cudaMemcpyHostToDevice));
@@ -515,7 +518,7 @@ int ptgpu_upload_static(
 
     // GPU traversal layout: a wide BVH per distinct BLAS + one static TLAS
     std::string err;
-    if(!build_wide_scene(nodes, n_nodes, links, indices, n_indices, pos, n_verts, instances, n_static, ctx->wide_host, err))
+    if(!build_wide_scene(nodes, n_nodes, links, indices, n_indices, pos, n_verts, instances, n_static, ctx->wide_host, err, meshes, n_meshes))
         return fail(ctx, "wide BVH build failed: %s", err.c_str());
     const WideScene& w = ctx->wide_host;
     CK(ctx->wnodes.reserve(w.nodes.size()));
@@ -540,6 +543,40 @@ int ptgpu_upload_static(
     return 0;
 }
 
+int ptgpu_upload_static(
+    ptgpu_ctx* ctx,
+    const ptgpu_bvh_node* nodes, size_t n_nodes,
+    const ptgpu_bvh_link* links, size_t n_links,
+    const uint32_t* indices, size_t n_indices,
+    const ptgpu_float3* pos, const ptgpu_float3* normal,
+    const ptgpu_float4* albedo, const ptgpu_float4* material, size_t n_verts,
+    const ptgpu_tlas_instance* instances, size_t n_static)
+{
+    if(!ctx) return 1;
+    if(!nodes || !links || !indices || !pos || !normal || !albedo || !material || !instances)
+        return fail(ctx, "ptgpu_upload_static: null array");
+    if(n_links != 8 * n_nodes) return fail(ctx, "ptgpu_upload_static: n_links (%zu) must be 8*n_nodes (%zu)", n_links, n_nodes);
+    if(n_static == 0 || n_nodes == 0) return fail(ctx, "ptgpu_upload_static: empty scene");
+    return upload_static_common(ctx, nodes, n_nodes, links, n_links, indices, n_indices, pos, normal, albedo, material, n_verts,
+                                instances, n_static, nullptr, 0);
+}
+
+int ptgpu_upload_meshes(
+    ptgpu_ctx* ctx,
+    const uint32_t* indices, size_t n_indices,
+    const ptgpu_float3* pos, const ptgpu_float3* normal,
+    const ptgpu_float4* albedo, const ptgpu_float4* material, size_t n_verts,
+    const ptgpu_mesh* meshes, size_t n_meshes,
+    const ptgpu_tlas_instance* instances, size_t n_static)
+{
+    if(!ctx) return 1;
+    if(!indices || !pos || !normal || !albedo || !material || !meshes || !instances)
+        return fail(ctx, "ptgpu_upload_meshes: null array");
+    if(n_static == 0 || n_meshes == 0) return fail(ctx, "ptgpu_upload_meshes: empty scene");
+    return upload_static_common(ctx, nullptr, 0, nullptr, 0, indices, n_indices, pos, normal, albedo, material, n_verts,
+                                instances, n_static, meshes, n_meshes);
+}
+
 int ptgpu_set_frame(
     ptgpu_ctx* ctx,
     const ptgpu_subframe* subframes, size_t n_subframes,
@@ -549,6 +586,7 @@ int ptgpu_set_frame(
 {
     if(!ctx) return 1;
     if(!ctx->have_static) return fail(ctx, "ptgpu_set_frame before ptgpu_upload_static");
+    if(!ctx->have_ref_bvh) return fail(ctx, "ptgpu_set_frame: the scene was built from meshes (no reference BVH); use ptgpu_set_frame_ranges");
     if(!subframes || n_subframes == 0) return fail(ctx, "ptgpu_set_frame: no subframes");
     if(!tlas_nodes || !tlas_links) return fail(ctx, "ptgpu_set_frame: null TLAS arrays");
     if(tlas_node_base != ctx->n_static_nodes)
@@ -705,6 +743,29 @@ int ptgpu_fetch_bmp(ptgpu_ctx* ctx, uint8_t* out_bmp)
     return 0;
 }
 
+int ptgpu_validate_frame(ptgpu_ctx* ctx, const uint8_t* ref_rgb_half, double* psnr, int32_t* good)
+{
+    if(!ctx || !ref_rgb_half || !psnr) return 1;
+    if(use(ctx)) return 1;
+    if(!ctx->render_pending) return fail(ctx, "ptgpu_validate_frame: no rendered frame on the device");
+    const uint32_t w = (uint32_t)ctx->cfg.width, h = (uint32_t)ctx->cfg.height, hw = (w + 1) / 2, hh = (h + 1) / 2;
+    const size_t ref_bytes = (size_t)hw * hh * 3;
+    CK(ctx->scratch_a.reserve(ref_bytes + 16));
+    CK(ctx->scratch_b.reserve(16));
+    CK(cudaMemcpyAsync(ctx->scratch_a.p, ref_rgb_half, ref_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemsetAsync(ctx->scratch_b.p, 0, 8, ctx->stream));
+    validate_psnr_kernel<<<ctx->sm_count * 2, 256, 0, ctx->stream>>>(ctx->out_bgra.p, w, h, (const uint8_t*)ctx->scratch_a.p, hw, hh,
+                                                                   (unsigned long long*)ctx->scratch_b.p);
+    unsigned long long sse = 0;
+    CK(cudaMemcpyAsync(&sse, ctx->scratch_b.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    // skimage.metrics.peak_signal_noise_ratio for uint8 images: data range 255, mean over all samples
+    const double mse = (double)sse / (double)ref_bytes;
+    *psnr = sse == 0 ? INFINITY : 10.0 * log10(255.0 * 255.0 / mse);
+    if(good) *good = *psnr >= 32.0 ? 1 : 0; // ACCEPT_MIN_PSNR, validator.py:11
+    return 0;
+}
+
 int ptgpu_render(ptgpu_ctx* ctx, uint8_t* out_bgra)
 {
     if(!out_bgra) return fail(ctx, "ptgpu_render: null output");
@@ -715,7 +776,7 @@ int ptgpu_render(ptgpu_ctx* ctx, uint8_t* out_bgra)
 int ptgpu_render_bmp(ptgpu_ctx* ctx, uint8_t* out_bmp)
 {
     if(!out_bmp) return fail(ctx, "ptgpu_render_bmp: null output");
-    if(render_full(ctx, false, true)) return 1;
+    if(render_full(ctx, true, true)) return 1; // the BGRA frame stays on the device for ptgpu_validate_frame
     return ptgpu_fetch_bmp(ctx, out_bmp);
 }
 
@@ -866,7 +927,9 @@ int ptgpu_pcg4d(ptgpu_ctx* ctx, uint32_t* states, size_t n, int32_t steps)
 int ptgpu_set_option(ptgpu_ctx* ctx, const char* key, int64_t value)
 {
     if(!ctx || !key) return 1;
-    if(!strcmp(key, "traversal")) { if(value != 0 && value != 1) return fail(ctx, "traversal must be 0 or 1"); ctx->traversal = (int)value; ctx->have_frame = false; return 0; }
+    if(!strcmp(key, "traversal")) { if(value != 0 && value != 1) return fail(ctx, "traversal must be 0 or 1");
+        if(value == 1 && ctx->have_static && !ctx->have_ref_bvh) return fail(ctx, "traversal 1 walks the reference's link tables: the scene was built from meshes");
+        ctx->traversal = (int)value; ctx->have_frame = false; return 0; }
     if(!strcmp(key, "counters")) { ctx->counters_on = value != 0; return 0; }
     if(!strcmp(key, "kernel")) { if(value < 0 || value > 2) return fail(ctx, "kernel must be 0, 1 or 2"); ctx->kernel = (int)value; return 0; }
     if(!strcmp(key, "bvh")) { if(value != 0 && value != 1) return fail(ctx, "bvh must be 0 or 1"); ctx->bvh = (int)value; return 0; }
@@ -921,6 +984,26 @@ int ptgpu_host_flatten_check(
     if(err && err_len) err[0] = 0;
     if(!nodes || !links || !indices || !pos || !instances || !out || n_links != 8 * n_nodes) e = "bad arguments";
     else if(build_wide_scene(nodes, n_nodes, links, indices, n_indices, pos, n_verts, instances, n_static, ws, e))
+    {
+        uint64_t bad = verify_wide_scene(ws, n_static, e);
+        out[0] = ws.blas.size(); out[1] = ws.nodes.size(); out[2] = ws.tris.size() / 3; out[3] = ws.tlas.size();
+        out[4] = ws.max_stack; out[5] = bad; out[6] = WIDE_STACK; out[7] = ws.cw_nodes.size() / 5;
+        if(bad == 0) return 0;
+    }
+    if(err && err_len) { strncpy(err, e.c_str(), err_len - 1); err[err_len - 1] = 0; }
+    return 1;
+}
+
+int ptgpu_host_build_check(
+    const uint32_t* indices, size_t n_indices, const ptgpu_float3* pos, size_t n_verts,
+    const ptgpu_mesh* meshes, size_t n_meshes,
+    const ptgpu_tlas_instance* instances, size_t n_static, uint64_t out[8], char* err, size_t err_len)
+{
+    std::string e;
+    WideScene ws;
+    if(err && err_len) err[0] = 0;
+    if(!indices || !pos || !meshes || !instances || !out || n_meshes == 0) e = "bad arguments";
+    else if(build_wide_scene(nullptr, 0, nullptr, indices, n_indices, pos, n_verts, instances, n_static, ws, e, meshes, n_meshes))
     {
         uint64_t bad = verify_wide_scene(ws, n_static, e);
         out[0] = ws.blas.size(); out[1] = ws.nodes.size(); out[2] = ws.tris.size() / 3; out[3] = ws.tlas.size();

@@ -71,6 +71,20 @@ class Renderer:
         self.n_static_nodes = nodes.shape[0]
         self.n_static = instances.shape[0]
 
+    def upload_meshes(self, indices, pos, normal, albedo, material, meshes, instances):
+        """ptgpu_upload_meshes: the static scene without the reference's BVH arrays; `meshes` is an
+        (n, 4) uint32 table of (vertex_count, triangle_count, index_offset, base_vertex_offset)."""
+        indices = _c(indices, np.uint32)
+        pos, normal = _c(pos, np.float32).reshape(-1, 4), _c(normal, np.float32).reshape(-1, 4)
+        albedo, material = _c(albedo, np.float32).reshape(-1, 4), _c(material, np.float32).reshape(-1, 4)
+        meshes = _c(meshes, np.uint32).reshape(-1, 4)
+        instances = _c(instances, np.uint8).reshape(-1, 160)
+        self._check(self.lib.ptgpu_upload_meshes(
+            self.ctx, _ptr(indices), indices.shape[0], _ptr(pos), _ptr(normal), _ptr(albedo), _ptr(material),
+            pos.shape[0], _ptr(meshes), meshes.shape[0], _ptr(instances), instances.shape[0]), "ptgpu_upload_meshes")
+        self.n_static_nodes = 0
+        self.n_static = instances.shape[0]
+
     def set_frame(self, subframes, dyn_instances, tlas_nodes, tlas_links, tlas_node_base=None):
         """Everything setup_animation_frame() produces (scene.cc:271-718)."""
         subframes = _c(subframes, np.uint8).reshape(-1, 160)
@@ -169,6 +183,17 @@ class Renderer:
         out = np.empty(n, np.uint8) if out is None else out
         self._check(self.lib.ptgpu_fetch_bmp(self.ctx, _ptr(out)), "ptgpu_fetch_bmp")
         return out
+
+    def validate_frame(self, ref_rgb_half):
+        """validator.py on the device-resident frame: (psnr, good) against the half-size RGB reference."""
+        ref = np.ascontiguousarray(ref_rgb_half, dtype=np.uint8)
+        hh, hw = (self.config.height + 1) // 2, (self.config.width + 1) // 2
+        if ref.shape != (hh, hw, 3):
+            raise ValueError("reference image must be %dx%dx3 uint8, got %r" % (hh, hw, ref.shape))
+        psnr = C.c_double()
+        good = C.c_int32()
+        self._check(self.lib.ptgpu_validate_frame(self.ctx, _ptr(ref), C.byref(psnr), C.byref(good)), "ptgpu_validate_frame")
+        return psnr.value, bool(good.value)
 
     def last_render_ms(self):
         ms = C.c_float()

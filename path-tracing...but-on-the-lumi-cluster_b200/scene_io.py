@@ -87,3 +87,13 @@ def available_frames(tag="testing"):
         if name.startswith("frame_%s_" % tag) and name.endswith(".npz"):
             out.append(int(name[len("frame_%s_" % tag):-4]))
     return out
+
+
+def mesh_table(instances, extra=()):
+    """(n, 4) uint32 table of the distinct meshes (vertex_count, triangle_count, index_offset,
+    base_vertex_offset) named by `instances` ((m, 160) uint8 tlas_instance records: bvh at byte 0, mesh at
+    byte 8, bvh.hh:69-81) plus `extra` rows (meshes only per-frame instances use), ordered by index_offset."""
+    inst = np.ascontiguousarray(instances, dtype=np.uint8).reshape(-1, 160)
+    rows = {tuple(int(x) for x in r) for r in inst[:, 8:24].copy().view(np.uint32).reshape(-1, 4)}
+    rows |= {tuple(int(x) for x in r) for r in extra}
+    return np.array(sorted(rows, key=lambda r: r[2]), dtype=np.uint32).reshape(-1, 4)

@@ -112,3 +112,42 @@ def test_scene_snapshot_roundtrip(pkg, oracle, tmp_path):
     assert st["links"].shape[0] == 8 * st["nodes"].shape[0]
     tl = fr["subframes"][:, :8].copy().view(np.uint32)      # subframe.tlas {node_count, node_offset}
     assert (tl[:, 1] >= st["nodes"].shape[0]).all()
+
+
+def _mesh_table(pkg, oracle, static):
+    names = ["logo", "buddha", "teapot", "armadillo", "dragon", "bunny", "end"]   # the per-frame meshes (scene.cc:634-674)
+    extra = [tuple(oracle.find_mesh(n)[:4]) for n in names]
+    return pkg.scene_io.mesh_table(static["instances"], extra)
+
+
+def test_own_blas_builder(pkg, oracle):
+    """ptgpu_upload_meshes' host side. Every BLAS built from the triangles alone (binned /
+    full-sweep SAH, optimal 8-wide collapse): each triangle of each mesh reachable exactly once, child
+    boxes enclose their subtrees, all static instances in the TLAS, stack bound within capacity."""
+    lib = pkg.load_library()
+    st = pkg.scene_io.static_from_view(oracle.setup_frame(0))
+    arrs = {k: np.ascontiguousarray(a) for k, a in st.items()}
+    meshes = _mesh_table(pkg, oracle, st)
+    assert meshes.shape[0] >= 14
+    out = (C.c_uint64 * 8)()
+    err = C.create_string_buffer(512)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+    rc = lib.ptgpu_host_build_check(
+        p(arrs["indices"]), arrs["indices"].shape[0], p(arrs["pos"]), arrs["pos"].shape[0],
+        p(meshes), meshes.shape[0], p(arrs["instances"]), arrs["instances"].shape[0], out, err, 512)
+    assert rc == 0, err.value
+    n_blas, _, n_tris, n_tlas, stack, bad, cap, n_cw = list(out)
+    assert n_blas == meshes.shape[0] and n_tris == int(meshes[:, 1].sum())
+    assert bad == 0 and 0 < stack <= cap and n_cw < n_tris
+    # a mesh that runs past the index buffer is refused, with a message
+    broken = meshes.copy()
+    broken[-1, 1] += 10 ** 6
+    rc = lib.ptgpu_host_build_check(
+        p(arrs["indices"]), arrs["indices"].shape[0], p(arrs["pos"]), arrs["pos"].shape[0],
+        p(broken), broken.shape[0], p(arrs["instances"]), arrs["instances"].shape[0], out, err, 512)
+    assert rc != 0 and b"index buffer" in err.value
+    # an instance whose mesh is not in the table is refused
+    rc = lib.ptgpu_host_build_check(
+        p(arrs["indices"]), arrs["indices"].shape[0], p(arrs["pos"]), arrs["pos"].shape[0],
+        p(meshes[1:]), meshes.shape[0] - 1, p(arrs["instances"]), arrs["instances"].shape[0], out, err, 512)
+    assert rc != 0 and b"does not match" in err.value

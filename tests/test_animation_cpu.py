@@ -29,10 +29,13 @@ def test_frame_state_matches_setup_animation_frame(pkg, oracle, anim):
         assert np.array_equal(dyn[:, :24], ref_dyn[:, :24]), f          # (bvh, mesh) handles: exact
         t, rt = dyn[:, 32:].copy().view(np.float32), ref_dyn[:, 32:].copy().view(np.float32)
         np.testing.assert_allclose(t, rt, rtol=2e-6, atol=3e-5)          # transform + inverse (coordinates ~100)
-        cam, rcam = sub[:, 16:104].copy().view(np.float32), ref_sub[:, 16:104].copy().view(np.float32)
+        # camera floats without the float3 padding lanes (the reference leaves those uninitialised)
+        keep = [0, 1, 2, 4, 5, 6, 8, 9, 10, 12, 13, 14, 16, 17, 18, 19, 21]
+        cam, rcam = sub[:, 16:104].copy().view(np.float32)[:, keep], ref_sub[:, 16:104].copy().view(np.float32)[:, keep]
         np.testing.assert_allclose(cam, rcam, rtol=2e-6, atol=3e-5)
         assert np.array_equal(sub[:, 96:100].copy().view(np.int32), ref_sub[:, 96:100].copy().view(np.int32))  # aperture_polygon
-        light, rlight = sub[:, 112:140].copy().view(np.float32), ref_sub[:, 112:140].copy().view(np.float32)
+        lk = [0, 1, 2, 4, 5, 6]
+        light, rlight = sub[:, 112:140].copy().view(np.float32)[:, lk], ref_sub[:, 112:140].copy().view(np.float32)[:, lk]
         np.testing.assert_allclose(light, rlight, rtol=0, atol=1e-6)
         # ranges: contiguous, in order, covering everything after the extras
         n_extra = int(b[0])

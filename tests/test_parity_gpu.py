@@ -404,3 +404,69 @@ def test_full_size_properties(frames, oracle):
     for y in (40, 180, 300):
         o_rgb, o_bgra = oracle.render_rect(0, y, 640, 1, 0, 256, 1)
         assert mae255(a[y:y + 1], o_bgra) <= 1.0
+
+
+def test_device_validator_matches_the_restated_validator(frames):
+    """ptgpu_validate_frame (validator.py:41-52 on the device-resident frame) against
+    oracle/validator_np.py on the fetched frame: same PSNR to rounding, same verdict. References: the
+    golden frame 0 downscaled (a GOOD case), the same with noise, and a wrong image (BAD)."""
+    from helpers import GOLDEN, read_bmp_rgb
+    from oracle import validator_np as V
+    r = frames.use(0)
+    own = r.render()[..., 2::-1]
+    gold_half = V.make_reference_png_array(read_bmp_rgb(GOLDEN))
+    rng = np.random.RandomState(11)
+    noisy = np.clip(gold_half.astype(np.int32) + rng.randint(-40, 41, gold_half.shape), 0, 255).astype(np.uint8)
+    wrong = rng.randint(0, 256, gold_half.shape).astype(np.uint8)
+    verdicts = []
+    for ref in (gold_half, noisy, wrong):
+        want_psnr, want_good = V.validate_frame(ref, own)
+        psnr, good = r.validate_frame(ref)
+        print("device validator: %.6f dB vs %.6f dB, good %s" % (psnr, want_psnr, good))
+        assert abs(psnr - want_psnr) <= 1e-9 * max(1.0, abs(want_psnr)) and good == want_good
+        verdicts.append(good)
+    assert verdicts[0] and not verdicts[2]
+    with pytest.raises(ValueError):
+        r.validate_frame(gold_half[:-1])
+
+
+def test_scene_from_meshes_gives_the_same_hits(pkg, oracle, renderer):
+    """ptgpu_upload_meshes (BLASes built here from the triangles, no reference BVH) against
+    ptgpu_upload_static (BLASes recovered from bvh.cc's arrays) and against the oracle's ray query: the
+    closest hit of a ray does not depend on the tree it was found with."""
+    from test_abi_cpu import _mesh_table
+    frame = 520
+    view = oracle.setup_frame(frame)
+    st = pkg.scene_io.static_from_view(view)
+    an = pkg.Animation(pkg.Config.testing())
+    sub, dyn, b, e = an.frame(frame)
+    own = pkg.Renderer(pkg.Config.testing(), device=0)
+    own.upload_meshes(st["indices"], st["pos"], st["normal"], st["albedo"], st["material"], _mesh_table(pkg, oracle, st), st["instances"])
+    own.set_frame_ranges(sub, dyn, b, e)
+    renderer.set_frame_ranges(sub, dyn, b, e)
+    rays = camera_like_rays(4000, frame)
+    f_ref, u_ref = renderer.trace_closest(rays, 0)
+    f_own, u_own = own.trace_closest(rays, 0)
+    assert (f_ref[:, 0] > 0).mean() > 0.5
+    assert np.array_equal(f_ref[:, 0] > 0, f_own[:, 0] > 0)
+    same = (u_ref[:, :2] == u_own[:, :2]).all(1)
+    print("own-built BLAS: %d rays, %d hits, same triangle %.4f, identical t %.4f" % (
+        len(rays), int((f_ref[:, 0] > 0).sum()), same.mean(), (f_ref[:, 0] == f_own[:, 0]).mean()))
+    assert same.all() and np.array_equal(f_ref, f_own)
+    o_ref = [oracle.trace_closest(x[0:3], x[4:7], float(x[3]), float(x[7]), 0) for x in rays[:400]]
+    o_t = np.array([h["thit"] for h in o_ref], np.float32)
+    hit = (o_t > 0) & (f_own[:400, 0] > 0)
+    assert ((o_t > 0) == (f_own[:400, 0] > 0)).mean() > 0.995
+    np.testing.assert_allclose(f_own[:400, 0][hit], o_t[hit], rtol=2e-4)
+    # whole-path check: the same window rendered with either tree
+    a_rgb, a_bgra = renderer.render_rect(200, 120, 96, 64, 0, 64, 4)
+    b_rgb, b_bgra = own.render_rect(200, 120, 96, 64, 0, 64, 4)
+    print("own-built BLAS window: identical pixels %.4f, MAE %.5f/255" % ((a_bgra == b_bgra).all(-1).mean(), mae255(a_bgra, b_bgra)))
+    assert mae255(a_bgra, b_bgra) <= 0.02
+    # what needs the reference's link tables says so
+    with pytest.raises(pkg.PtgpuError):
+        own.set_option("traversal", 1)
+    with pytest.raises(pkg.PtgpuError):
+        own.set_frame(**pkg.scene_io.frame_from_view(view))
+    own.close()
+    an.close()
