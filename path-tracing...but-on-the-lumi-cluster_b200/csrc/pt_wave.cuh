@@ -92,6 +92,33 @@ PT_D void wf_append(uint32_t* q, uint32_t* count, bool pred, uint32_t val)
     if(pred) q[base + __popc(m & ((1u << lane) - 1u))] = val;
 }
 
+// Block-aggregated append: one atomic per block and call instead of one per warp (1.8 M per round on one
+// address with per-warp appends). Must be reached by every thread of the block the same number of times;
+// `s_tmp` is WARPS + 1 words of shared memory per call site. Block order = warp order = slot order.
+template<int WARPS>
+PT_D void wf_append_block(uint32_t* q, uint32_t* count, bool pred, uint32_t val, uint32_t* s_tmp)
+{
+    const unsigned m = __ballot_sync(0xFFFFFFFFu, pred);
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    if(lane == 0u) s_tmp[warp] = (uint32_t)__popc(m);
+    __syncthreads();
+    if(threadIdx.x == 0)
+    {
+        uint32_t total = 0;
+        #pragma unroll
+        for(int k = 0; k < WARPS; ++k) total += s_tmp[k];
+        s_tmp[WARPS] = total ? atomicAdd(count, total) : 0u;
+    }
+    __syncthreads();
+    if(pred)
+    {
+        uint32_t base = s_tmp[WARPS];
+        for(unsigned k = 0; k < warp; ++k) base += s_tmp[k];
+        q[base + __popc(m & ((1u << lane) - 1u))] = val;
+    }
+    __syncthreads();
+}
+
 // ---- init: every slot starts idle; valid ones are queued for their first sample ---------------
 __global__ void wf_init_kernel(WaveBuffers wb, RenderJob job)
 {
@@ -116,7 +143,8 @@ wf_generate_kernel(Scene sc, RenderJob job, WaveBuffers wb)
     // Scans all slots in slot order (pixel tiles), so the primary rays of one 2x2-pixel block and one
     // motion-blur subframe land next to each other in the primary segment.
     if(wb.cnt->n_new == 0u) return;
-    const uint32_t rounded = (wb.n_slots + 31u) & ~31u;
+    __shared__ uint32_t s_tmp[9];
+    const uint32_t rounded = (wb.n_slots + 255u) & ~255u;   // whole blocks: every thread of a block loops equally often
     for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < rounded; i += gridDim.x * blockDim.x)
     {
         const uint32_t slot = i;
@@ -143,7 +171,7 @@ wf_generate_kernel(Scene sc, RenderJob job, WaveBuffers wb)
             wb.nee[slot] = make_float4(0, 0, 0, 0);
             wb.cursor[slot] = make_int2(k, 0);
         }
-        wf_append(wb.q_trace + WF_SEG_PRIMARY * (size_t)wb.seg_cap, &wb.cnt->n_seg[WF_SEG_PRIMARY], ok, slot);
+        wf_append_block<8>(wb.q_trace + WF_SEG_PRIMARY * (size_t)wb.seg_cap, &wb.cnt->n_seg[WF_SEG_PRIMARY], ok, slot, s_tmp);
     }
 }
 
@@ -690,7 +718,8 @@ wf_shade_kernel(Scene sc, RenderJob job, WaveBuffers wb)
 {
     const uint32_t n = FAR ? wb.cnt->n_far : wb.cnt->n_near;
     const uint32_t* q = FAR ? wb.q_far : wb.q_near;
-    const uint32_t rounded = (n + 31u) & ~31u;
+    __shared__ uint32_t s_tmp[2][5];
+    const uint32_t rounded = (n + 127u) & ~127u;   // whole blocks (block-aggregated appends below)
     for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < rounded; i += gridDim.x * blockDim.x)
     {
         const uint32_t slot = i < n ? q[i] : WF_INVALID;
@@ -787,9 +816,10 @@ wf_shade_kernel(Scene sc, RenderJob job, WaveBuffers wb)
                 push_shadow = lit;
             }
         }
-        wf_append(wb.q_trace + WF_SEG_SHADOW * (size_t)wb.seg_cap, &wb.cnt->n_seg[WF_SEG_SHADOW], push_shadow, slot | WF_SHADOW_BIT);
-        wf_append(wb.q_trace + WF_SEG_BOUNCE * (size_t)wb.seg_cap, &wb.cnt->n_seg[WF_SEG_BOUNCE], push_ext, slot);
-        if(__any_sync(0xFFFFFFFFu, push_new) && (threadIdx.x & 31u) == 0u) atomicAdd(&wb.cnt->n_new, 1u);
+        wf_append_block<4>(wb.q_trace + WF_SEG_SHADOW * (size_t)wb.seg_cap, &wb.cnt->n_seg[WF_SEG_SHADOW], push_shadow, slot | WF_SHADOW_BIT, s_tmp[0]);
+        wf_append_block<4>(wb.q_trace + WF_SEG_BOUNCE * (size_t)wb.seg_cap, &wb.cnt->n_seg[WF_SEG_BOUNCE], push_ext, slot, s_tmp[1]);
+        // n_new is a flag (wf_generate only asks whether it is non-zero): a plain store, not an atomic per warp
+        if(__any_sync(0xFFFFFFFFu, push_new) && (threadIdx.x & 31u) == 0u) wb.cnt->n_new = 1u;
     }
 }
 
