@@ -86,12 +86,14 @@ PT_D void shade_hit(const Scene& sc, const Light& light, const Hit& h, v3 origin
     const RefInstance* in = sc.instances + h.inst;
     const uint2 mo = __ldg(reinterpret_cast<const uint2*>(in) + 2); // index_offset, base_vertex
     const float4 t0 = __ldg(&in->transform[0]), t1 = __ldg(&in->transform[1]), t2 = __ldg(&in->transform[2]);
-    const uint32_t* ip = sc.indices + mo.x + h.prim * 3u;
-    const uint32_t i0 = mo.y + __ldg(ip), i1 = mo.y + __ldg(ip + 1), i2 = mo.y + __ldg(ip + 2);
     const float bx = h.u, by = h.v, bz = 1.0f - h.u - h.v;
-    const float4 n0 = __ldg(sc.normal + i0), n1 = __ldg(sc.normal + i1), n2 = __ldg(sc.normal + i2);
-    const float4 a0 = __ldg(sc.albedo + i0), a1 = __ldg(sc.albedo + i1), a2 = __ldg(sc.albedo + i2);
-    const float4 m0 = __ldg(sc.material + i0), m1 = __ldg(sc.material + i1), m2 = __ldg(sc.material + i2);
+    // the reference gathers 3 indices, then 9 attribute vectors through them (path_tracer.hh:375-409): two
+    // dependent levels of scattered 16-byte loads. shade_tris holds the same nine vectors per triangle,
+    // contiguous (144 B), one level after the instance record.
+    const float4* rec = sc.shade_tris + 9 * (size_t)(mo.x / 3u + h.prim);
+    const float4 n0 = __ldg(rec), n1 = __ldg(rec + 1), n2 = __ldg(rec + 2);
+    const float4 a0 = __ldg(rec + 3), a1 = __ldg(rec + 4), a2 = __ldg(rec + 5);
+    const float4 m0 = __ldg(rec + 6), m1 = __ldg(rec + 7), m2 = __ldg(rec + 8);
     v3 n = mk3(n0) * bx + mk3(n1) * by + mk3(n2) * bz;
     m3 rot; rot.c0 = mk3(t0); rot.c1 = mk3(t1); rot.c2 = mk3(t2);
     n = normalize(mul_m3v3(rot, n)); // forward 3x3, not the inverse transpose (:371,392)

@@ -82,6 +82,9 @@ struct Scene
     const float4* normal;
     const float4* albedo;
     const float4* material;
+    // per triangle of the index buffer (triangle k = indices[3k..3k+2] + its mesh's base vertex), the nine
+    // attribute vectors shade_hit interpolates, gathered once at upload: n0 n1 n2 a0 a1 a2 m0 m1 m2
+    const float4* shade_tris;
     const RefInstance* instances;   // [0,n_static) static, then this frame's dynamic instances
     const RefSubframe* subframes;
     // wide layout

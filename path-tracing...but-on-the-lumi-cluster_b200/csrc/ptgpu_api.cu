@@ -71,6 +71,7 @@ struct ptgpu_ctx
     DevBuf<uint2> ref_links;
     DevBuf<uint32_t> indices;
     DevBuf<float4> pos, normal, albedo, material;
+    DevBuf<float4> shade_tris;      // 9 per triangle of the index buffer (pt_scene.cuh)
     DevBuf<RefInstance> instances; // static + dynamic
     size_t n_static_nodes = 0, n_static = 0, n_verts = 0, n_indices = 0;
     bool have_static = false;
@@ -163,6 +164,7 @@ Scene make_scene(ptgpu_ctx* ctx)
     s.ref_links = ctx->ref_links.p;
     s.indices = ctx->indices.p;
     s.pos = ctx->pos.p; s.normal = ctx->normal.p; s.albedo = ctx->albedo.p; s.material = ctx->material.p;
+    s.shade_tris = ctx->shade_tris.p;
     s.instances = ctx->instances.p;
     s.subframes = ctx->subframes.p;
     s.wnodes = ctx->wnodes.p; s.wtris = ctx->wtris.p; s.wblas = ctx->wblas.p; s.winst = ctx->winst.p;
@@ -463,7 +465,7 @@ void ptgpu_destroy(ptgpu_ctx* ctx)
     ctx->ref_nodes.release(); ctx->ref_links.release(); ctx->indices.release();
     ctx->pos.release(); ctx->normal.release(); ctx->albedo.release(); ctx->material.release();
     ctx->instances.release(); ctx->wnodes.release(); ctx->wtris.release(); ctx->wblas.release();
-    ctx->winst.release(); ctx->wtlas.release(); ctx->cwnodes.release(); ctx->cwtris.release(); ctx->cw_inst_index.release(); ctx->subframes.release(); ctx->dyn_range.release();
+    ctx->winst.release(); ctx->wtlas.release(); ctx->cwnodes.release(); ctx->cwtris.release(); ctx->shade_tris.release(); ctx->cw_inst_index.release(); ctx->subframes.release(); ctx->dyn_range.release();
     ctx->out_bgra.release(); ctx->out_bmp.release(); ctx->out_rgb.release(); ctx->counters.release();
     ctx->mega_state.release(); ctx->wave_mem.release(); ctx->wave_flag.release();
     if(ctx->wave_flag_host) cudaFreeHost(ctx->wave_flag_host);
@@ -521,6 +523,27 @@ static int upload_static_common(
     if(!build_wide_scene(nodes, n_nodes, links, indices, n_indices, pos, n_verts, instances, n_static, ctx->wide_host, err, meshes, n_meshes))
         return fail(ctx, "wide BVH build failed: %s", err.c_str());
     const WideScene& w = ctx->wide_host;
+    {   // shading records: the nine attribute vectors of every triangle, contiguous (pt_scene.cuh)
+        std::vector<float4> rec(9 * (n_indices / 3), make_float4(0.f, 0.f, 0.f, 0.f));
+        for(const WideBlasInfo& bi : w.blas_info)
+        {
+            if(bi.mesh.index_offset % 3u) return fail(ctx, "mesh index_offset %u is not a multiple of 3", bi.mesh.index_offset);
+            for(uint32_t t = 0; t < bi.mesh.triangle_count; ++t)
+            {
+                const size_t k = bi.mesh.index_offset / 3u + t;
+                for(int j = 0; j < 3; ++j)
+                {
+                    const size_t v = (size_t)bi.mesh.base_vertex_offset + indices[3 * k + j];
+                    const ptgpu_float3& n = normal[v];
+                    rec[9 * k + j] = make_float4(n.x, n.y, n.z, 0.f);
+                    rec[9 * k + 3 + j] = make_float4(albedo[v].x, albedo[v].y, albedo[v].z, albedo[v].w);
+                    rec[9 * k + 6 + j] = make_float4(material[v].x, material[v].y, material[v].z, material[v].w);
+                }
+            }
+        }
+        CK(ctx->shade_tris.reserve(rec.size() + 1));
+        CK(cudaMemcpy(ctx->shade_tris.p, rec.data(), rec.size() * sizeof(float4), cudaMemcpyHostToDevice));
+    }
     CK(ctx->wnodes.reserve(w.nodes.size()));
     CK(ctx->wtris.reserve(w.tris.size()));
     CK(ctx->wblas.reserve(w.blas.size()));
