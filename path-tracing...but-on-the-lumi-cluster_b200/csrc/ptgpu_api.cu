@@ -715,7 +715,7 @@ static int render_full(ptgpu_ctx* ctx, bool bgra, bool bmp)
     job.out_bgra = bgra ? ctx->out_bgra.p : nullptr;
     job.out_bmp = bmp ? ctx->out_bmp.p : nullptr;
     job.bmp_pitch = ctx->bmp_pitch;
-    job.min_active = ctx->min_active < 0 ? (ctx->kernel == 2 ? 8 : 0) : ctx->min_active;
+    job.min_active = ctx->min_active < 0 ? (ctx->kernel == 2 ? 6 : 0) : ctx->min_active;
     int launches = 0;
     CK(cudaEventRecord(ctx->ev_begin, ctx->stream));
     if(bmp && !ctx->bmp_header_done)
@@ -853,7 +853,7 @@ int ptgpu_render_rect(
     job.x0 = x0; job.y0 = y0; job.w = w; job.h = h;
     job.s_begin = s_begin; job.s_count = s_count; job.s_stride = s_stride;
     job.out_rgb = ctx->out_rgb.p; job.out_bgra = d_bgra; job.out_bmp = nullptr; job.bmp_pitch = 0;
-    job.min_active = ctx->min_active < 0 ? (ctx->kernel == 2 ? 8 : 0) : ctx->min_active;
+    job.min_active = ctx->min_active < 0 ? (ctx->kernel == 2 ? 6 : 0) : ctx->min_active;
     CK(cudaEventRecord(ctx->ev_begin, ctx->stream));
     int l = launch_job(ctx, job);
     if(l < 0) { tmp_bgra.release(); return fail(ctx, "kernel launch failed: %s", cudaGetErrorString(cudaGetLastError())); }
