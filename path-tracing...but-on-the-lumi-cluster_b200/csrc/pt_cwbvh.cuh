@@ -62,15 +62,25 @@ PT_D uint32_t sign_extend_s8x4(uint32_t x)
     return r;
 }
 
+PT_D float rcp_approx(float x)
+{
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
 PT_D void cw_set_space(CwState& st, v3 o, v3 d)
 {
     st.o = o;
     // a zero component would give inf * 0 = NaN against the quantised grid: clamp to +-1e-20
     const float eps = 1e-20f;
-    // MUFU.RCP (1 ulp) is enough here: the quantised child boxes carry far more slack than that
-    st.idir = mk3(__frcp_rn(fabsf(d.x) > eps ? d.x : copysignf(eps, d.x)),
-                  __frcp_rn(fabsf(d.y) > eps ? d.y : copysignf(eps, d.y)),
-                  __frcp_rn(fabsf(d.z) > eps ? d.z : copysignf(eps, d.z)));
+    // MUFU.RCP alone (1 ulp, rcp.approx) is enough here: the quantised child boxes carry far more slack
+    // than that, and the box test already runs against a 1e-5 longer ray. The IEEE-rounded __frcp_rn
+    // this replaces compiled to ~30 instructions per component (Newton step + special cases) and made
+    // cw_set_space 3.8 % of all instructions of the traversal kernel.
+    st.idir = mk3(rcp_approx(fabsf(d.x) > eps ? d.x : copysignf(eps, d.x)),
+                  rcp_approx(fabsf(d.y) > eps ? d.y : copysignf(eps, d.y)),
+                  rcp_approx(fabsf(d.z) > eps ? d.z : copysignf(eps, d.z)));
     st.sign_bits = (d.x < 0.0f ? 1u : 0u) | (d.y < 0.0f ? 2u : 0u) | (d.z < 0.0f ? 4u : 0u);
     // slot bit 4 = +x side, 2 = +y, 1 = +z; a ray going +x meets the -x children first
     const uint32_t oct = (d.x < 0.0f ? 0u : 4u) | (d.y < 0.0f ? 0u : 2u) | (d.z < 0.0f ? 0u : 1u);
