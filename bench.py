@@ -60,36 +60,72 @@ def traversal_flops_table():
 
 
 class ClockSampler(threading.Thread):
-    """Samples SM clock and throttle reasons with nvidia-smi while the timed region runs."""
+    """Samples SM clock and throttle reasons while the timed region runs: through NVML in-process
+    (nvidia_ml_py), falling back to one nvidia-smi process per sample. (Forking nvidia-smi five times a
+    second from a process that maps a CUDA context cost the timed loop ~5 ms per step.)"""
 
-    def __init__(self, index):
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
+
+    def __init__(self, index, uuid=None):
         super().__init__(daemon=True)
         self.index = index
         self.stop_flag = threading.Event()
         self.samples, self.reasons, self.max_mhz = [], set(), None
+        self.source = "nvidia-smi"
+        self.nvml = self.handle = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = None
+            if uuid:
+                try:
+                    h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + str(uuid)).encode())
+                except Exception:
+                    h = None
+            self.handle = h if h is not None else pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+            self.source = "nvml"
+        except Exception:
+            self.nvml = self.handle = None
 
-    def run(self):
+    def sample_nvml(self):
+        n = self.nvml
+        self.samples.append(float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)))
+        get = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or n.nvmlDeviceGetCurrentClocksThrottleReasons
+        mask = int(get(self.handle))
+        for name, bit in self.REASONS:
+            if mask & bit:
+                self.reasons.add(name)
+
+    def sample_smi(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                              "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+        f = [x.strip() for x in out.strip().split(",")]
+        self.samples.append(float(f[0]))
+        self.max_mhz = float(f[1])
+        for n, v in zip(names, f[2:]):
+            if v.lower().startswith("active"):
+                self.reasons.add(n)
+
+    def run(self):
         while not self.stop_flag.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                f = [x.strip() for x in out.strip().split(",")]
-                self.samples.append(float(f[0]))
-                self.max_mhz = float(f[1])
-                for n, v in zip(names, f[2:]):
-                    if v.lower().startswith("active"):
-                        self.reasons.add(n)
+                if self.nvml is not None:
+                    self.sample_nvml()
+                else:
+                    self.sample_smi()
             except Exception:
                 pass
-            self.stop_flag.wait(0.2)
+            self.stop_flag.wait(float(os.environ.get("BENCH_SAMPLER_PERIOD", "0.1" if self.nvml is not None else "0.5")))
 
     def result(self):
         s = sorted(self.samples)
         return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz,
-                "reasons": sorted(self.reasons), "samples": len(s)}
+                "reasons": sorted(self.reasons), "samples": len(s), "source": self.source}
 
 
 def cpu_sample_rows():
@@ -259,7 +295,7 @@ def main():
         r.render_async()
         r.sync()
 
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(local_rank, getattr(torch.cuda.get_device_properties(local_rank), "uuid", None))
     sampler.start()
 
     # ---- loop A: device-resident. Static scene in HBM; per step ~40 KB of per-frame transforms go up,
@@ -269,11 +305,16 @@ def main():
     dev_ms, launches, flops = 0.0, 0, 0.0
     trace_us, trace_launches, trace_flops = 0.0, 0, 0.0
     ftab, ttab = flops_table(), traversal_flops_table()
+    trace_steps = os.environ.get("BENCH_TRACE_STEPS") and rank == 0
+    step_wall = []
     for i in range(args.steps):
+        ts = time.perf_counter()
         f = frame_of(i)
         set_frame(f)
         r.render_async()
         ms, n = r.last_render_ms()   # waits for this frame's end event
+        if trace_steps:
+            print("step %d frame %d: wall %.2f ms, device %.2f ms" % (i, f, 1e3 * (time.perf_counter() - ts), ms), file=sys.stderr)
         dev_ms += ms
         launches += n
         flops += ftab.get(f, 0.0) * PATHS_PER_FRAME
@@ -281,8 +322,12 @@ def main():
         trace_us += r.get_stat("trace_us")
         trace_launches += r.get_stat("trace_launches")
         trace_flops += ttab.get(f, 0.0) * PATHS_PER_FRAME
+        step_wall.append(1e3 * (time.perf_counter() - ts))
+    t_loop = time.perf_counter() - t0
     barrier()
     wall_a = time.perf_counter() - t0
+    if trace_steps:
+        print("steps %.2f ms, loop %.2f ms, with closing barrier %.2f ms" % (sum(step_wall), 1e3 * t_loop, 1e3 * wall_a), file=sys.stderr)
 
     # ---- loop B: end to end through the C ABI call a drop-in user makes (ptgpu_render_frame): host
     #      arrays in (subframes, dynamic instances, reference TLAS arrays), pinned BGRA frame out.
@@ -335,6 +380,7 @@ def main():
             "config": workload_config(world, args.animation),
             "animation_seconds_estimate": round(ANIMATION_FRAMES * (wall_a / args.steps) / world, 1),
             "device_ms_per_step": round(1e3 * dev_s / args.steps, 3),
+            "timing_breakdown_ms": {"sum_of_steps": round(sum(step_wall), 2), "loop": round(1e3 * t_loop, 2), "with_closing_barrier": round(1e3 * wall_a, 2)},
             "e2e": {"value": round(e2e, 2), "unit": "Mpaths/s", "h2d_bytes_per_step": int(h2d / args.steps),
                     "d2h_bytes_per_step": WIDTH * HEIGHT * 4, "ms_per_step": round(1e3 * wall_b / args.steps, 3),
                     "call": "ptgpu_anim_frame + ptgpu_set_frame_ranges + ptgpu_render" if args.animation else "ptgpu_render_frame (include/ptgpu.h)"},
