@@ -375,7 +375,10 @@ wf_trace_kernel(Scene sc, RenderJob job, WaveBuffers wb)
 //   * leaving an instance is free: the world-space ray constants are parked under the exit marker;
 //   * a lane whose query ends takes the next ray from the global queue (refill when >= min_active
 //     lanes are idle), closest-hit and shadow rays alike.
-constexpr int CW_PEND = 4;
+#ifndef CW_PEND_N
+#define CW_PEND_N 4
+#endif
+constexpr int CW_PEND = CW_PEND_N;
 
 #ifndef WF_CW_BLOCKS
 #define WF_CW_BLOCKS 7
