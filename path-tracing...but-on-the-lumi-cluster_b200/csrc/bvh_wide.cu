@@ -1052,18 +1052,38 @@ bool build_wide_scene(
     auto emit_inst = [](const std::vector<uint32_t>& ids) -> uint32_t { return 0x80000000u | ids[0]; };
     uint32_t tstack = collapse_tree(ttree, 1, out.tlas, emit_inst);
     {
+        // compressed TLAS: without the world-space start instance, if the scene has one
+        if(CW_WORLD_START && n_static > 1)
+        {
+            uint32_t best_tris = 0;
+            for(size_t i = 0; i < n_static; ++i)
+            {
+                const ptgpu_float4* c = instances[i].transform.r;
+                const bool identity =
+                    c[0].x == 1.f && c[0].y == 0.f && c[0].z == 0.f && c[1].x == 0.f && c[1].y == 1.f && c[1].z == 0.f &&
+                    c[2].x == 0.f && c[2].y == 0.f && c[2].z == 1.f && c[3].x == 0.f && c[3].y == 0.f && c[3].z == 0.f;
+                const uint32_t tris = out.blas[out.instances[i].blas].tri_count;
+                if(identity && tris >= 1024u && tris > best_tris) { best_tris = tris; out.cw_world_inst = (uint32_t)i; }
+            }
+        }
+        std::vector<Prim> cprims;
+        for(const Prim& pr : prims) if(pr.id != out.cw_world_inst) cprims.push_back(pr);
+        std::vector<TNode> ctree(1);
+        ctree.reserve(2 * cprims.size());
+        build_sah(cprims, 0, cprims.size(), ctree, 0);
         auto emit_inst_cw = [&](const std::vector<uint32_t>& ids) -> uint32_t {
             const uint32_t first = (uint32_t)out.cw_inst_index.size();
             for(uint32_t id : ids) out.cw_inst_index.push_back(id);
             return first;
         };
         uint32_t depth = 0;
-        out.cw_tlas_root = build_cw_tree(ttree, 1, out.cw_nodes, emit_inst_cw, depth, err);
+        out.cw_tlas_root = build_cw_tree(ctree, 1, out.cw_nodes, emit_inst_cw, depth, err);
         if(out.cw_tlas_root == 0xFFFFFFFFu) { err = "compressed TLAS: " + err; return false; }
         // per node visit at most two pushes (rest of the node group, postponed leaf group); entering an
         // instance pushes the rest of its group and the exit marker; one entry for the dynamic instances
         // (+2: the world-space ray constants parked under the exit marker by the wavefront kernel)
-        out.cw_max_stack = 2 * depth + 4 + 2 * cw_blas_depth + 1;
+        // (+4: the TLAS root group and the parked constants + marker of the world-space start instance)
+        out.cw_max_stack = 2 * depth + 4 + 2 * cw_blas_depth + 1 + 4;
         if(out.cw_max_stack > (uint32_t)CW_STACK)
         {
             err = "compressed traversal stack bound " + std::to_string(out.cw_max_stack) + " exceeds CW_STACK";
@@ -1234,6 +1254,7 @@ uint64_t verify_wide_scene(const WideScene& ws, size_t n_static, std::string& er
         }
         std::vector<uint32_t> seen(n_static, 0);
         walk_cw(ws.cw_tlas_root, true, seen, 0, (uint32_t)n_static);
+        if(ws.cw_world_inst < n_static) seen[ws.cw_world_inst]++; // not a TLAS leaf: every query starts inside it
         for(uint32_t c : seen) if(c != 1) { fail("compressed TLAS: instance missing or duplicated"); break; }
     }
     return bad;

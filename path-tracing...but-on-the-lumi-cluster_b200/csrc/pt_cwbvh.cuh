@@ -157,7 +157,9 @@ PT_D void cw_intersect_node(const float4* __restrict__ nodes, uint32_t node_inde
 
 // Query start: the subframe's dynamic instances (world-box test) go on the stack as one instance
 // group, then the static TLAS root is the first node group.
-template<class Stack>
+// PARKED: the caller's exit protocol keeps the world-space ray constants under the exit marker
+// (wf_trace_cw_kernel); otherwise the marker alone (cw_pop_phase recomputes them).
+template<bool PARKED, class Stack>
 PT_D void cw_begin(const Scene& sc, CwState& st, Stack& stack, uint32_t subframe, v3 ro, v3 rd,
                    float tmin, float tmax, bool any)
 {
@@ -175,8 +177,26 @@ PT_D void cw_begin(const Scene& sc, CwState& st, Stack& stack, uint32_t subframe
         if(box_hit(__ldg(&wi->lo), __ldg(&wi->hi), ro, st.idir, tmin, tmax)) mask |= 1u << k;
     }
     if(mask) stack.set(st.sp++, make_uint2(0x80000000u, mask));
-    st.ngroup = make_uint2(sc.cw_tlas_root, 0x80000000u);
     st.tgroup = make_uint2(0u, 0u);
+    if(sc.cw_world_inst == 0xFFFFFFFFu)
+    {
+        st.ngroup = make_uint2(sc.cw_tlas_root, 0x80000000u);
+        return;
+    }
+    // The query starts INSIDE the world-space instance (identity transform: the terrain, 28 % of all
+    // instance entries when it was a TLAS leaf): no transform, no entry step, and its hit shortens the
+    // ray before the TLAS is walked. The TLAS root group waits on the stack under the exit marker.
+    stack.set(st.sp++, make_uint2(sc.cw_tlas_root, 0x80000000u));
+    if(PARKED)
+    {
+        stack.set(st.sp++, make_uint2(__float_as_uint(st.idir.x), __float_as_uint(st.idir.y)));
+        stack.set(st.sp++, make_uint2(__float_as_uint(st.idir.z), (st.oct_inv4 & 0xFFu) | (st.sign_bits << 8)));
+    }
+    stack.set(st.sp++, make_uint2(CW_MARK_X, 0u));
+    tri_preprocess(rd, st.axis, st.S);
+    st.in_blas = true;
+    st.cur_inst = sc.cw_world_inst;
+    st.ngroup = make_uint2(sc.cw_world_root, 0x80000000u);
 }
 
 PT_D uint32_t cw_decode_instance(const Scene& sc, const CwState& st, uint32_t base, uint32_t bit)
@@ -293,7 +313,7 @@ PT_D bool trace_cw(const Scene& sc, uint32_t subframe, v3 origin, v3 dir, float 
     uint2 stack_mem[CW_STACK];
     LocalStack stack{stack_mem};
     CwState st;
-    cw_begin(sc, st, stack, subframe, origin, dir, tmin, tmax, ANY);
+    cw_begin<false>(sc, st, stack, subframe, origin, dir, tmin, tmax, ANY);
     for(;;)
     {
         cw_node_phase(sc, st, stack);

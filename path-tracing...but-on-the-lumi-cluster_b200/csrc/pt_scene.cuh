@@ -99,6 +99,8 @@ struct Scene
     const float4* cwtris;           // 3 float4 per triangle, leaf order; p0.w = primitive id (bits)
     const uint32_t* cw_inst_index;  // TLAS leaf order -> instance index
     uint32_t cw_tlas_root;
+    uint32_t cw_world_inst;         // static instance every query starts in (identity transform), or 0xFFFFFFFF
+    uint32_t cw_world_root;         // its BLAS root in cwnodes
     uint32_t n_static;
     uint32_t n_subframes;
     // config

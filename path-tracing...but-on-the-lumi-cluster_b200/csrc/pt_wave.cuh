@@ -443,7 +443,7 @@ wf_trace_cw_kernel(Scene sc, RenderJob job, WaveBuffers wb)
                     const float4 fd = shadow ? wb.shadow_d[slot] : wb.ray_d[slot];
                     const int sample = job.s_begin + wb.cursor[slot].x * job.s_stride;
                     const uint32_t subframe = sample < 0 ? 0u : (uint32_t)sample / (uint32_t)sc.samples_per_subframe;
-                    cw_begin(sc, st, stack, subframe, mk3(fo.x, fo.y, fo.z), mk3(fd.x, fd.y, fd.z), fo.w, PT_MAX_RAY_DIST, shadow);
+                    cw_begin<true>(sc, st, stack, subframe, mk3(fo.x, fo.y, fo.z), mk3(fd.x, fd.y, fd.z), fo.w, PT_MAX_RAY_DIST, shadow);
                     np = 0;
                     active = true;
                 }

@@ -171,6 +171,8 @@ Scene make_scene(ptgpu_ctx* ctx)
     s.wtlas = ctx->wtlas.p; s.dyn_range = ctx->dyn_range.p;
     s.cwnodes = ctx->cwnodes.p; s.cwtris = ctx->cwtris.p; s.cw_inst_index = ctx->cw_inst_index.p;
     s.cw_tlas_root = ctx->wide_host.cw_tlas_root;
+    s.cw_world_inst = ctx->wide_host.cw_world_inst;
+    s.cw_world_root = s.cw_world_inst != 0xFFFFFFFFu ? ctx->wide_host.instances[s.cw_world_inst].cw_root : 0u;
     s.n_static = (uint32_t)ctx->n_static;
     s.n_subframes = (uint32_t)ctx->n_subframes;
     s.width = ctx->cfg.width; s.height = ctx->cfg.height;
