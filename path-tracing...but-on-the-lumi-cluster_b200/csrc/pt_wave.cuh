@@ -375,6 +375,9 @@ wf_trace_kernel(Scene sc, RenderJob job, WaveBuffers wb)
 //   * leaving an instance is free: the world-space ray constants are parked under the exit marker;
 //   * a lane whose query ends takes the next ray from the global queue (refill when >= min_active
 //     lanes are idle), closest-hit and shadow rays alike.
+#ifndef WF_INSTANCES_FIRST
+#define WF_INSTANCES_FIRST 0
+#endif
 #ifndef CW_PEND_N
 #define CW_PEND_N 4
 #endif
@@ -512,7 +515,11 @@ wf_trace_cw_kernel(Scene sc, RenderJob job, WaveBuffers wb)
             if(st.tgroup.y != 0u)
             {
                 if(st.in_blas) { pend[(np++) * WF_TRACE_THREADS] = st.tgroup; st.tgroup.y = 0u; }              // triangles wait for the TRI block
+#if WF_INSTANCES_FIRST
+                else if(st.ngroup.y > 0x00FFFFFFu) { stack.set(st.sp++, st.ngroup); st.ngroup.y = 0u; } // the node's inner children wait below its instances
+#else
                 else if(st.ngroup.y > 0x00FFFFFFu) { stack.set(st.sp++, st.tgroup); st.tgroup.y = 0u; } // instances wait below the TLAS nodes
+#endif
             }
         };
         auto tri_step = [&]() {
