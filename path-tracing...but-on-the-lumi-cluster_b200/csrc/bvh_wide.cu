@@ -8,8 +8,12 @@
 //     bvh.cc:181), siblings are contiguous in BFS numbering, each child's `cancel` is the
 //     previous sibling and the first stored child's `cancel` is the parent's `cancel`;
 //   - a leaf has bit 31 of `accept` set, the rest is the triangle index (bvh.cc:176-177).
-// The binary SAH tree with multi-way terminal nodes (bvh.cc:113-142) is then collapsed into
-// 4-wide nodes whose leaves hold up to WIDE_LEAF_MAX pre-gathered triangles.
+// The binary SAH tree with multi-way terminal nodes (bvh.cc:113-142) is then collapsed twice: into
+// compressed 8-wide nodes with one triangle per leaf child (the default traversal; cost-optimal
+// collapse, OptimalCollapser) and into 4-wide float nodes whose leaves hold up to WIDE_LEAF_MAX
+// pre-gathered triangles (tile kernel / megakernel). Without reference BVH arrays
+// (ptgpu_upload_meshes) the binary tree of each mesh is built here instead (build_mesh_tree).
+// One static TLAS over tight world boxes of the static instances completes the scene.
 #include "bvh_wide.hh"
 
 #include <algorithm>

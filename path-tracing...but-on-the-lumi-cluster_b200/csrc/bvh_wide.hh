@@ -1,6 +1,7 @@
 // Host side of the GPU acceleration layout: flattens the reference's link-table BVHs
-// (bvh.hh:35-67, built by bvh.cc:43-229) into 4-wide nodes with multi-triangle leaves and
-// pre-gathered triangle vertices, and builds one static TLAS over the static instances.
+// (bvh.hh:35-67, built by bvh.cc:43-229), or builds BLASes from the triangles, into compressed
+// 8-wide nodes (and 4-wide float nodes for the older kernels) with pre-gathered triangle
+// vertices, and builds one static TLAS over the static instances.
 #pragma once
 #include "../../include/ptgpu.h"
 #include "pt_scene.cuh"
