@@ -299,6 +299,26 @@ int ptgpu_set_animation_frame(ptgpu_ctx* ctx, const ptgpu_anim* anim, uint32_t f
  * traversal launches "trace_us" covers). */
 int ptgpu_get_stat(ptgpu_ctx* ctx, const char* key, uint64_t* out);
 
+/* ---- OBJ/MTL loader: load_mesh, mesh.cc:104-265, without the reference's mesh.cc ----- */
+
+/* A growing set of mesh buffers = `mesh_buffers` (mesh.hh:31-43): every ptgpu_meshes_load_obj appends one
+ * mesh's indices and de-duplicated vertices and returns its handle (`mesh`, mesh.hh:18-28). Same parsing
+ * rules, vertex numbering and attribute packing as the reference, so the arrays can be handed to
+ * ptgpu_upload_meshes (or to the reference's own build_blas). Host-only, needs no GPU. Errors (missing OBJ
+ * or MTL file) return non-zero with ptgpu_meshes_last_error(); the reference prints and exits (mesh.cc:25-29). */
+typedef struct ptgpu_mesh_set ptgpu_mesh_set;
+int ptgpu_meshes_create(ptgpu_mesh_set** out);
+void ptgpu_meshes_destroy(ptgpu_mesh_set* set);
+const char* ptgpu_meshes_last_error(const ptgpu_mesh_set* set);
+int ptgpu_meshes_load_obj(ptgpu_mesh_set* set, const char* obj_path, ptgpu_mesh* out_mesh);
+size_t ptgpu_meshes_index_count(const ptgpu_mesh_set* set);
+size_t ptgpu_meshes_vertex_count(const ptgpu_mesh_set* set);
+const uint32_t* ptgpu_meshes_indices(const ptgpu_mesh_set* set);      /* valid until the next load / destroy */
+const ptgpu_float3* ptgpu_meshes_pos(const ptgpu_mesh_set* set);
+const ptgpu_float3* ptgpu_meshes_normal(const ptgpu_mesh_set* set);
+const ptgpu_float4* ptgpu_meshes_albedo(const ptgpu_mesh_set* set);
+const ptgpu_float4* ptgpu_meshes_material(const ptgpu_mesh_set* set);
+
 /* Host-only, needs no GPU: runs the BVH flattening that ptgpu_upload_static performs on the
  * reference arrays (bvh.cc:43-229 output) and checks the result structurally (every triangle
  * reachable exactly once, boxes nested, every static instance in the TLAS once).

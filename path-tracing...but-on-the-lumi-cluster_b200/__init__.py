@@ -10,3 +10,4 @@ from . import scene_io  # noqa: F401
 from . import sharding  # noqa: F401
 from . import capi  # noqa: F401
 from .animation import Animation  # noqa: F401
+from .meshes import MeshSet  # noqa: F401

@@ -17,6 +17,9 @@ SYMBOLS = [
     "ptgpu_last_render_ms", "ptgpu_set_option", "ptgpu_read_counters", "ptgpu_scene_stats",
     "ptgpu_host_flatten_check", "ptgpu_get_stat", "ptgpu_validate_frame",
     "ptgpu_upload_meshes", "ptgpu_host_build_check",
+    "ptgpu_meshes_create", "ptgpu_meshes_destroy", "ptgpu_meshes_last_error", "ptgpu_meshes_load_obj",
+    "ptgpu_meshes_index_count", "ptgpu_meshes_vertex_count", "ptgpu_meshes_indices", "ptgpu_meshes_pos",
+    "ptgpu_meshes_normal", "ptgpu_meshes_albedo", "ptgpu_meshes_material",
     "ptgpu_anim_create", "ptgpu_anim_destroy", "ptgpu_anim_subframe_count", "ptgpu_anim_max_instances",
     "ptgpu_anim_frame_count", "ptgpu_anim_frame", "ptgpu_set_animation_frame",
 ]
@@ -113,9 +116,24 @@ def load_library():
     L.ptgpu_upload_meshes.argtypes = [vp, vp, sz, vp, vp, vp, vp, sz, vp, sz, vp, sz]
     L.ptgpu_host_build_check.argtypes = [vp, sz, vp, sz, vp, sz, vp, sz, C.POINTER(C.c_uint64), C.c_char_p, sz]
     L.ptgpu_validate_frame.argtypes = [vp, vp, C.POINTER(C.c_double), C.POINTER(C.c_int32)]
+    L.ptgpu_meshes_create.argtypes = [C.POINTER(vp)]
+    L.ptgpu_meshes_destroy.argtypes = [vp]
+    L.ptgpu_meshes_destroy.restype = None
+    L.ptgpu_meshes_last_error.argtypes = [vp]
+    L.ptgpu_meshes_last_error.restype = C.c_char_p
+    L.ptgpu_meshes_load_obj.argtypes = [vp, C.c_char_p, vp]
+    for fn in ("ptgpu_meshes_index_count", "ptgpu_meshes_vertex_count"):
+        getattr(L, fn).argtypes = [vp]
+        getattr(L, fn).restype = sz
+    for fn in ("ptgpu_meshes_indices", "ptgpu_meshes_pos", "ptgpu_meshes_normal", "ptgpu_meshes_albedo", "ptgpu_meshes_material"):
+        getattr(L, fn).argtypes = [vp]
+        getattr(L, fn).restype = vp
+    untyped = ("ptgpu_default_config", "ptgpu_destroy", "ptgpu_last_error", "ptgpu_bmp_size", "ptgpu_anim_destroy",
+               "ptgpu_anim_subframe_count", "ptgpu_anim_max_instances", "ptgpu_anim_frame_count", "ptgpu_meshes_destroy",
+               "ptgpu_meshes_last_error", "ptgpu_meshes_index_count", "ptgpu_meshes_vertex_count", "ptgpu_meshes_indices",
+               "ptgpu_meshes_pos", "ptgpu_meshes_normal", "ptgpu_meshes_albedo", "ptgpu_meshes_material")
     for name in SYMBOLS:
-        if name not in ("ptgpu_default_config", "ptgpu_destroy", "ptgpu_last_error", "ptgpu_bmp_size", "ptgpu_anim_destroy",
-                        "ptgpu_anim_subframe_count", "ptgpu_anim_max_instances", "ptgpu_anim_frame_count"):
+        if name not in untyped:
             getattr(L, name).restype = C.c_int
     _lib = L
     return L
