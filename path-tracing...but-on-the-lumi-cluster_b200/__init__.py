@@ -11,3 +11,4 @@ from . import sharding  # noqa: F401
 from . import capi  # noqa: F401
 from .animation import Animation  # noqa: F401
 from .meshes import MeshSet  # noqa: F401
+from . import validate  # noqa: F401
