@@ -23,7 +23,10 @@ namespace pt {
 // CW_SM_STACK entries in shared memory laid out [entry][thread] (bank = thread, conflict-free for any
 // mix of depths), the rest in local memory. ncu on the all-local version: the loads of the stack top
 // and of the pending-triangle list were the top three stall sites of wf_trace_cw (25 % of samples).
-constexpr int CW_SM_STACK = 14;
+#ifndef CW_SM_STACK_N
+#define CW_SM_STACK_N 14
+#endif
+constexpr int CW_SM_STACK = CW_SM_STACK_N;
 struct LocalStack
 {
     uint2* p;

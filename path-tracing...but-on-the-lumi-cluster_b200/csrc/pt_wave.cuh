@@ -177,7 +177,10 @@ wf_generate_kernel(Scene sc, RenderJob job, WaveBuffers wb)
 
 // ---- trace: persistent traversal kernel -----------------------------------------------------------
 constexpr int WF_TRACE_THREADS = 128;
-constexpr int WF_FETCH_CHUNK = 64;
+#ifndef WF_FETCH_CHUNK_N
+#define WF_FETCH_CHUNK_N 64
+#endif
+constexpr int WF_FETCH_CHUNK = WF_FETCH_CHUNK_N;
 
 __global__ void __launch_bounds__(WF_TRACE_THREADS, 6)
 wf_trace_kernel(Scene sc, RenderJob job, WaveBuffers wb)

@@ -211,6 +211,9 @@ void wave_timing(ptgpu_ctx* ctx)
 
 // Carves the wavefront pool out of one allocation and runs rounds of generate / trace / shade until
 // no slot has a ray or a sample left. Returns kernels launched, or -1.
+#ifndef WF_SHADE_GRID
+#define WF_SHADE_GRID 8   // blocks per SM of the shade kernels (4 resident at 106 registers: two waves)
+#endif
 int launch_wave(ptgpu_ctx* ctx, const Scene& sc, RenderJob job)
 {
     const int tiles_x = (job.w + WF_TILE - 1) / WF_TILE, tiles_y = (job.h + WF_TILE - 1) / WF_TILE;
@@ -281,8 +284,8 @@ int launch_wave(ptgpu_ctx* ctx, const Scene& sc, RenderJob job)
             if(ctx->validate && ctx->bvh == 1) wf_validate_kernel<<<sms * 8, 128, 0, st>>>(sc, job, wb, wb.stats);
             wf_phase_kernel<<<1, 32, 0, st>>>(wb, 1, nullptr);
             wf_classify_kernel<<<sms * 8, 256, 0, st>>>(wb);
-            wf_shade_kernel<true><<<sms * 8, 128, 0, st>>>(sc, job, wb);
-            wf_shade_kernel<false><<<sms * 8, 128, 0, st>>>(sc, job, wb);
+            wf_shade_kernel<true><<<sms * WF_SHADE_GRID, 128, 0, st>>>(sc, job, wb);
+            wf_shade_kernel<false><<<sms * WF_SHADE_GRID, 128, 0, st>>>(sc, job, wb);
             if(timed) cudaEventRecord(ctx->wave_events[3 * rounds + 2], st);
             wf_phase_kernel<<<1, 32, 0, st>>>(wb, 2, ctx->wave_flag.p);
             launches += 7;
