@@ -744,6 +744,20 @@ struct CwEmitter
                 meta[s] = (uint8_t)((((1u << cnt) - 1u) << 5) | off);
             }
         }
+#if CW_PAD_EMPTY
+        {   // empty slots: inverted box + the meta byte of a real child (pt_scene.cuh)
+            static_assert(CW_LEAF_MAX == 1, "CW_PAD_EMPTY needs one triangle per leaf child");
+            int first_used = -1;
+            for(int s = 0; s < CW_WIDTH && first_used < 0; ++s) if(child_in_slot[s] >= 0) first_used = s;
+            if(first_used < 0) { err = "node without children"; return 0; }
+            for(int s = 0; s < CW_WIDTH; ++s)
+            {
+                if(child_in_slot[s] >= 0) continue;
+                for(int a = 0; a < 3; ++a) { qlo[a][s] = 255; qhi[a][s] = 0; }
+                meta[s] = meta[first_used];
+            }
+        }
+#endif
         // pass 2: inner children, stored contiguously from child_base in slot order
         uint32_t deepest = 0, inner_rank = 0;
         for(int s = 0; s < CW_WIDTH; ++s)
@@ -1195,6 +1209,10 @@ uint64_t verify_wide_scene(const WideScene& ws, size_t n_static, std::string& er
             {
                 const uint32_t meta = (metaw[s >> 2] >> (8 * (s & 3))) & 0xFF;
                 if(meta == 0) { if(imask & (1u << s)) fail("imask set on an empty slot"); continue; }
+                bool padding = false;   // CW_PAD_EMPTY: an empty slot is an inverted box
+                for(int a = 0; a < 3; ++a)
+                    if(((q[a][s >> 2] >> (8 * (s & 3))) & 0xFF) > ((q[3 + a][s >> 2] >> (8 * (s & 3))) & 0xFF)) padding = true;
+                if(padding) { if(imask & (1u << s)) fail("imask set on a padding slot"); continue; }
                 Box cb;
                 for(int a = 0; a < 3; ++a)
                 {

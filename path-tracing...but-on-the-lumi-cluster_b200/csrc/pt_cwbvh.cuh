@@ -133,7 +133,9 @@ PT_D void cw_intersect_node(const float4* __restrict__ nodes, uint32_t node_inde
         const uint32_t is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
         const uint32_t inner_mask4 = sign_extend_s8x4(is_inner4 << 3);
         const uint32_t bit_index4 = (meta4 ^ (st.oct_inv4 & inner_mask4)) & 0x1F1F1F1Fu;
+#if !CW_PAD_EMPTY
         const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
+#endif
         const uint32_t qlx = __float_as_uint(half ? n2.y : n2.x), qly = __float_as_uint(half ? n2.w : n2.z);
         const uint32_t qlz = __float_as_uint(half ? n3.y : n3.x), qhx = __float_as_uint(half ? n3.w : n3.z);
         const uint32_t qhy = __float_as_uint(half ? n4.y : n4.x), qhz = __float_as_uint(half ? n4.w : n4.z);
@@ -148,8 +150,13 @@ PT_D void cw_intersect_node(const float4* __restrict__ nodes, uint32_t node_inde
             const float t0z = fmaf(u8f_near(z_near, j), az, oz), t1z = fmaf(u8f_far(z_far, j), az, oz);
             const float cmin = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, st.tmin));
             const float cmax = fminf(fminf(t1x, t1y), fminf(t1z, tmax_box));
+#if CW_PAD_EMPTY
+            // every slot holds a real child or an inverted box: no validity mask (the shift uses the low 5 bits)
+            if(cmin <= cmax) hitmask |= 1u << ((bit_index4 >> (8 * j)) & 31u);
+#else
             if(cmin <= cmax)
                 hitmask |= ((child_bits4 >> (8 * j)) & 0xFFu) << ((bit_index4 >> (8 * j)) & 0xFFu);
+#endif
         }
     }
     ngroup.x = __float_as_uint(n1.x);

@@ -3,6 +3,13 @@
 #include "pt_math.cuh"
 #include "pt_shade.cuh"
 
+// Compressed 8-wide nodes: 1 = the empty child slots of a node carry an INVERTED box (lo 255, hi 0: no ray
+// passes the slab test) and the meta byte of one of the node's real children, so the box test needs no
+// per-child validity mask: a child that passes sets bit (1 << its index). Needs one triangle per leaf child.
+#ifndef CW_PAD_EMPTY
+#define CW_PAD_EMPTY 1
+#endif
+
 namespace pt {
 
 // ---- reference-layout records read on the device (layouts: include/ptgpu.h) -------------------
