@@ -411,7 +411,8 @@ void build_mesh_tree(const uint32_t* indices, const ptgpu_float3* pos, const ptg
 //   n2  qlo.x[0..7] | qlo.y[0..7]             child boxes, 8 bits per bound: lo = p + q * 2^e
 //   n3  qlo.z[0..7] | qhi.x[0..7]
 //   n4  qhi.y[0..7] | qhi.z[0..7]
-// meta[slot]: inner child 0b001_11sss (24 + slot); leaf 0b{unary count}_{offset from tri_base}; 0 = empty.
+// meta[slot]: inner child 0b001_11sss (24 + slot); leaf 0b{unary count}_{offset from tri_base}; 0 = empty —
+// or, with CW_PAD_EMPTY (pt_scene.cuh), an empty slot holds an inverted box and a copy of a real child's meta.
 // Children sit in the slot whose octant direction best matches their offset from the node centre, so
 // a ray visits slots in the order (slot XOR ray octant), high to low, without sorting distances.
 
