@@ -147,6 +147,11 @@ int ptgpu_set_frame(
     const ptgpu_bvh_node* tlas_nodes, const ptgpu_bvh_link* tlas_links,
     size_t n_tlas_nodes, size_t tlas_node_base);
 
+/* A subframe may see at most this many per-frame instances (shared prefix + its own range): the traversal
+ * kernels keep them as one bit group / 16 stack entries. The reference animation uses at most 7
+ * (scene.cc:634-674). More is an error, not a silent truncation. */
+#define PTGPU_MAX_DYNAMIC_PER_SUBFRAME 16
+
 /* Same without reference TLAS arrays: the caller states each subframe's dynamic range
  * [dyn_begin[i], dyn_end[i]) into dyn_instances (what scene.cc:651-678 keeps in `entries`).
  * subframes[i].tlas is ignored. */
@@ -230,6 +235,13 @@ int ptgpu_last_render_ms(ptgpu_ctx* ctx, float* ms, int32_t* launches);
  *              reference link tables; only with traversal = 1
  * "kernel":    2 = wavefront (default), 0 = persistent megakernel, 1 = one-thread-per-path tile kernel
  * "bvh":       1 = compressed 8-wide BVH (default, wavefront only), 0 = 4-wide float BVH
+ * "flat":      1 (default) = the static instances are traversed as ONE world-space BVH over all their
+ *              triangles, built at upload (no instancing for the static part: 180 GB of HBM make the 15.6 M
+ *              instanced triangles of the shipped scene a 1 GB array); 0 = static TLAS + instanced BLASes.
+ *              Set it before the scene is uploaded. Per-frame instances are instances either way.
+ * "sort":      1 (default) = the wavefront renderer sorts bounce and shadow rays by direction octant and
+ *              origin cell before every traversal launch; 0 = queue order.
+ * "top_smem":  1 = the traversal kernel stages the top levels of the flat BVH in shared memory (default 0).
  * "lanes", "pool_budget_mb": path slots per pixel of the wavefront pool (power of two) and its budget
  * "min_active", "node_threshold", "node_burst", "tri_threshold", "xform_threshold": warp scheduling
  *              of the traversal kernels (see csrc/pt_wave.cuh); results do not depend on them
@@ -295,8 +307,9 @@ int ptgpu_set_animation_frame(ptgpu_ctx* ctx, const ptgpu_anim* anim, uint32_t f
  * every round is re-traced with the plain single-ray traversal and compared with what the scheduled
  * traversal kernel stored; the number of disagreeing queries), "trace_us" / "shade_us" (device time
  * of the traversal launches, and of the classify + shade launches, of that frame, from CUDA events
- * recorded on the render stream around them; first 48 rounds) and "trace_launches" (how many
- * traversal launches "trace_us" covers). */
+ * recorded on the render stream around them; first 48 rounds), "trace_launches" (how many
+ * traversal launches "trace_us" covers), "sort_us" (ray sort + camera-ray generation of the same rounds).
+ * About the uploaded scene: "flat_tris", "flat_nodes", "flat_depth", "flat_build_ms" (0 without a flat scene). */
 int ptgpu_get_stat(ptgpu_ctx* ctx, const char* key, uint64_t* out);
 
 /* ---- OBJ/MTL loader: load_mesh, mesh.cc:104-265, without the reference's mesh.cc ----- */
@@ -324,6 +337,14 @@ const ptgpu_float4* ptgpu_meshes_material(const ptgpu_mesh_set* set);
  * reachable exactly once, boxes nested, every static instance in the TLAS once).
  * out = {BLAS count, wide nodes, triangles, TLAS nodes, stack bound, violations, stack capacity, 0}. */
 int ptgpu_host_flatten_check(
+    const ptgpu_bvh_node* nodes, size_t n_nodes, const ptgpu_bvh_link* links, size_t n_links,
+    const uint32_t* indices, size_t n_indices, const ptgpu_float3* pos, size_t n_verts,
+    const ptgpu_tlas_instance* instances, size_t n_static, uint64_t out[8], char* err, size_t err_len);
+/* Host-only: builds the flat static scene (all static instances as world-space triangles under ONE
+ * compressed 8-wide BVH, no instancing; replaces the per-subframe build_tlas of bvh.cc:252-284 for the
+ * static part) from the same arrays and checks it structurally.
+ * out = {triangles, nodes, top-tree nodes, depth, violations, build milliseconds, 0, 0}. */
+int ptgpu_host_flat_check(
     const ptgpu_bvh_node* nodes, size_t n_nodes, const ptgpu_bvh_link* links, size_t n_links,
     const uint32_t* indices, size_t n_indices, const ptgpu_float3* pos, size_t n_verts,
     const ptgpu_tlas_instance* instances, size_t n_static, uint64_t out[8], char* err, size_t err_len);

@@ -19,8 +19,14 @@
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
+#include <atomic>
+#include <chrono>
+#include <deque>
 #include <functional>
+#include <mutex>
+#include <thread>
 
 namespace pt {
 namespace {
@@ -281,6 +287,63 @@ uint32_t collapse_tree(const std::vector<TNode>& tree, int leaf_max, std::vector
 
 struct Prim { Box box; uint32_t id; };
 
+// Split of a large range by 32 centroid bins per axis (O(n) per level instead of three sorts): partitions
+// prims[begin, end) in place and returns the split position (never begin or end).
+size_t binned_split(std::vector<Prim>& prims, size_t begin, size_t end)
+{
+    const size_t n = end - begin;
+    size_t best_split = begin + n / 2;
+    constexpr int BINS = 32;
+    float clo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, chi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    for(size_t i = begin; i < end; ++i)
+        for(int a = 0; a < 3; ++a)
+        {
+            const float c = prims[i].box.lo[a] + prims[i].box.hi[a];
+            clo[a] = std::min(clo[a], c); chi[a] = std::max(chi[a], c);
+        }
+    float best_cost = FLT_MAX; int best_axis = -1, best_bin = 0;
+    for(int a = 0; a < 3; ++a)
+    {
+        const float ext = chi[a] - clo[a];
+        if(!(ext > 0.0f)) continue;
+        const float scale = (float)BINS / ext;
+        Box bb[BINS]; uint32_t cnt[BINS] = {};
+        for(int k = 0; k < BINS; ++k) bb[k].reset();
+        for(size_t i = begin; i < end; ++i)
+        {
+            const int k = std::min(BINS - 1, (int)((prims[i].box.lo[a] + prims[i].box.hi[a] - clo[a]) * scale));
+            bb[k].grow(prims[i].box); cnt[k]++;
+        }
+        float right_area[BINS]; uint32_t right_cnt[BINS];
+        Box acc; acc.reset(); uint32_t c = 0;
+        for(int k = BINS - 1; k > 0; --k) { if(cnt[k]) acc.grow(bb[k]); c += cnt[k]; right_area[k] = c ? acc.area() : 0.0f; right_cnt[k] = c; }
+        acc.reset(); c = 0;
+        for(int k = 1; k < BINS; ++k)
+        {
+            if(cnt[k - 1]) acc.grow(bb[k - 1]);
+            c += cnt[k - 1];
+            if(c == 0 || right_cnt[k] == 0) continue;
+            const float cost = acc.area() * (float)c + right_area[k] * (float)right_cnt[k];
+            if(cost < best_cost) { best_cost = cost; best_axis = a; best_bin = k; }
+        }
+    }
+    if(best_axis >= 0)
+    {
+        const int a = best_axis;
+        const float scale = (float)BINS / (chi[a] - clo[a]), lo = clo[a];
+        auto mid = std::partition(prims.begin() + begin, prims.begin() + end, [&](const Prim& x) {
+            return std::min(BINS - 1, (int)((x.box.lo[a] + x.box.hi[a] - lo) * scale)) < best_bin;
+        });
+        best_split = (size_t)(mid - prims.begin());
+    }
+    if(best_axis < 0 || best_split == begin || best_split == end)
+    {   // all centroids coincide: halve the range in primitive order
+        std::sort(prims.begin() + begin, prims.begin() + end, [](const Prim& x, const Prim& y) { return x.id < y.id; });
+        best_split = begin + n / 2;
+    }
+    return best_split;
+}
+
 // Binary SAH tree over `prims`, single-primitive leaves. Ranges of at most `sweep_below` primitives are
 // split by the full sweep (every split position on every axis, as bvh.cc:43-140 does); larger ranges by
 // 32 centroid bins per axis, which costs O(n) per level instead of three sorts.
@@ -324,57 +387,7 @@ void build_sah(std::vector<Prim>& prims, size_t begin, size_t end, std::vector<T
             return cx < cy || (cx == cy && x.id < y.id);
         });
     }
-    else
-    {
-        constexpr int BINS = 32;
-        float clo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, chi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
-        for(size_t i = begin; i < end; ++i)
-            for(int a = 0; a < 3; ++a)
-            {
-                const float c = prims[i].box.lo[a] + prims[i].box.hi[a];
-                clo[a] = std::min(clo[a], c); chi[a] = std::max(chi[a], c);
-            }
-        float best_cost = FLT_MAX; int best_axis = -1, best_bin = 0;
-        for(int a = 0; a < 3; ++a)
-        {
-            const float ext = chi[a] - clo[a];
-            if(!(ext > 0.0f)) continue;
-            const float scale = (float)BINS / ext;
-            Box bb[BINS]; uint32_t cnt[BINS] = {};
-            for(int k = 0; k < BINS; ++k) bb[k].reset();
-            for(size_t i = begin; i < end; ++i)
-            {
-                const int k = std::min(BINS - 1, (int)((prims[i].box.lo[a] + prims[i].box.hi[a] - clo[a]) * scale));
-                bb[k].grow(prims[i].box); cnt[k]++;
-            }
-            float right_area[BINS]; uint32_t right_cnt[BINS];
-            Box acc; acc.reset(); uint32_t c = 0;
-            for(int k = BINS - 1; k > 0; --k) { if(cnt[k]) acc.grow(bb[k]); c += cnt[k]; right_area[k] = c ? acc.area() : 0.0f; right_cnt[k] = c; }
-            acc.reset(); c = 0;
-            for(int k = 1; k < BINS; ++k)
-            {
-                if(cnt[k - 1]) acc.grow(bb[k - 1]);
-                c += cnt[k - 1];
-                if(c == 0 || right_cnt[k] == 0) continue;
-                const float cost = acc.area() * (float)c + right_area[k] * (float)right_cnt[k];
-                if(cost < best_cost) { best_cost = cost; best_axis = a; best_bin = k; }
-            }
-        }
-        if(best_axis >= 0)
-        {
-            const int a = best_axis;
-            const float scale = (float)BINS / (chi[a] - clo[a]), lo = clo[a];
-            auto mid = std::partition(prims.begin() + begin, prims.begin() + end, [&](const Prim& x) {
-                return std::min(BINS - 1, (int)((x.box.lo[a] + x.box.hi[a] - lo) * scale)) < best_bin;
-            });
-            best_split = (size_t)(mid - prims.begin());
-        }
-        if(best_axis < 0 || best_split == begin || best_split == end)
-        {   // all centroids coincide: halve the range in primitive order
-            std::sort(prims.begin() + begin, prims.begin() + end, [](const Prim& x, const Prim& y) { return x.id < y.id; });
-            best_split = begin + n / 2;
-        }
-    }
+    else best_split = binned_split(prims, begin, end);
     const uint32_t first = (uint32_t)tree.size();
     tree.emplace_back(); tree.emplace_back();
     tree[self].first = first; tree[self].count = 2;
@@ -422,7 +435,7 @@ struct W8Child
     int inner = -1;                 // index into the W8 node list, or -1
     std::vector<uint32_t> leaves;   // payloads when inner < 0
 };
-struct W8Node { Box box; std::vector<W8Child> ch; };
+struct W8Node { Box box; std::vector<W8Child> ch; int stub = -1; };   // stub >= 0: placeholder for the root of separately emitted subtree `stub`
 
 struct GItem { Box box; int32_t src = -1; std::vector<uint32_t> leaves; int nested = -1; };
 
@@ -668,11 +681,13 @@ struct CwEmitter
     std::function<uint32_t(const std::vector<uint32_t>&)> emit_leaf; // appends leaf payloads, returns first index
     uint32_t max_depth = 0;
     std::string err;
+    std::vector<std::pair<uint32_t, int>> stubs;   // (node index, subtree) of every placeholder met
 
     // Fills node `cw` (already allocated) from w8[wi]; returns the depth below.
     uint32_t emit(int wi, uint32_t cw)
     {
         const W8Node& n = w8[wi];
+        if(n.stub >= 0) { stubs.push_back({cw, n.stub}); return 0; }
         const int k = (int)n.ch.size();
         if(k > CW_WIDTH) { err = "node wider than 8"; return 0; }
         // greedy slot assignment: child with the best alignment to a free slot's octant direction first
@@ -858,6 +873,104 @@ void pad_world_box(float lo[3], float hi[3])
     }
     const float pad = 1e-5f * extent + 1e-6f * mag;
     for(int k = 0; k < 3; ++k) { lo[k] -= pad; hi[k] += pad; }
+}
+
+
+// ---- flat static scene: one compressed 8-wide BVH over the world-space triangles of all static instances ----
+//
+// The reference keeps every object as an instance of its mesh (bvh.cc:252-284) and so did the first
+// version of this library. The static part of the scene is a forest: 884 trees and rocks whose boxes
+// overlap each other and the terrain, so a ray entered 2.35 instances on average and 16 % of the entries
+// hit nothing below the BLAS root. With 180 GB of HBM the instancing buys nothing: the 15.6 M instanced
+// triangles are 750 MB as world-space vertices + 250 MB of nodes, and one SAH tree over all of them has
+// no instance overlap, no ray transform and no second stack level. Per-frame instances (<= 7 hero
+// objects, motion-blurred) stay instances.
+//
+// Build: primitives are split top-down (binned SAH) into ranges of at most FLAT_RANGE triangles; the ranges
+// are built, collapsed and emitted in parallel with the BLAS code path; a small top tree over the ranges is
+// collapsed on its own and its leaf slots are filled with copies of the subtree root nodes.
+
+constexpr size_t FLAT_RANGE = 96 * 1024;
+
+template<class F>
+void parallel_for(size_t n, unsigned threads, F&& fn)
+{
+    if(threads <= 1 || n <= 1) { for(size_t i = 0; i < n; ++i) fn(i); return; }
+    std::atomic<size_t> next{0};
+    std::vector<std::thread> pool;
+    const unsigned t = (unsigned)std::min<size_t>(threads, n);
+    for(unsigned k = 0; k < t; ++k)
+        pool.emplace_back([&]() { for(size_t i; (i = next.fetch_add(1)) < n;) fn(i); });
+    for(auto& th : pool) th.join();
+}
+
+struct FlatRange { size_t begin, end; };
+
+struct FlatTop
+{
+    std::deque<TNode> nodes;          // stable references while other threads append
+    std::vector<FlatRange> ranges;
+    std::mutex mu;
+    uint32_t alloc2() { std::lock_guard<std::mutex> g(mu); nodes.emplace_back(); nodes.emplace_back(); return (uint32_t)nodes.size() - 2; }
+    uint32_t add_range(size_t b, size_t e) { std::lock_guard<std::mutex> g(mu); ranges.push_back({b, e}); return (uint32_t)ranges.size() - 1; }
+    TNode& at(uint32_t i) { std::lock_guard<std::mutex> g(mu); return nodes[i]; }
+};
+
+void split_top(std::vector<Prim>& prims, size_t begin, size_t end, FlatTop& top, uint32_t self, bool parallel)
+{
+    Box b; b.reset();
+    for(size_t i = begin; i < end; ++i) b.grow(prims[i].box);
+    TNode& me = top.at(self);
+    me.box = b;
+    if(end - begin <= FLAT_RANGE)
+    {
+        me.count = 0;
+        me.payload = top.add_range(begin, end);
+        return;
+    }
+    const size_t mid = binned_split(prims, begin, end);
+    const uint32_t first = top.alloc2();
+    me.first = first; me.count = 2;
+    if(parallel && end - begin > 8 * FLAT_RANGE)
+    {
+        std::thread left([&]() { split_top(prims, begin, mid, top, first, true); });
+        split_top(prims, mid, end, top, first + 1, true);
+        left.join();
+    }
+    else
+    {
+        split_top(prims, begin, mid, top, first, parallel);
+        split_top(prims, mid, end, top, first + 1, parallel);
+    }
+}
+
+// Moves the nodes [0, count) of a compressed tree whose root is node 0 into breadth-first order, so that
+// "index < K" selects its top levels (the traversal kernel can stage those in shared memory).
+void cw_breadth_first(std::vector<float4>& nodes, uint32_t count, const std::vector<std::pair<uint32_t, int>>& stubs,
+                      std::vector<std::pair<uint32_t, int>>& stubs_out)
+{
+    std::vector<uint8_t> is_stub(count, 0);
+    for(const auto& sb : stubs) is_stub[sb.first] = 1;
+    std::vector<float4> out(5 * (size_t)count);
+    std::vector<uint32_t> new_of(count, 0xFFFFFFFFu);
+    std::vector<uint32_t> queue{0u};
+    new_of[0] = 0;
+    uint32_t next = 1;
+    for(size_t q = 0; q < queue.size(); ++q)
+    {
+        const uint32_t old = queue[q], nw = new_of[old];
+        for(int k = 0; k < 5; ++k) out[5 * (size_t)nw + k] = nodes[5 * (size_t)old + k];
+        if(is_stub[old]) continue;
+        const uint32_t imask = f2u(nodes[5 * (size_t)old].w) >> 24, kids = (uint32_t)__builtin_popcount(imask);
+        if(kids == 0) continue;
+        const uint32_t base = f2u(nodes[5 * (size_t)old + 1].x);
+        out[5 * (size_t)nw + 1].x = u2f(next);
+        for(uint32_t j = 0; j < kids; ++j) { new_of[base + j] = next + j; queue.push_back(base + j); }
+        next += kids;
+    }
+    stubs_out.clear();
+    for(const auto& sb : stubs) stubs_out.push_back({new_of[sb.first], sb.second});
+    for(size_t i = 0; i < out.size(); ++i) nodes[i] = out[i];
 }
 
 } // namespace
@@ -1119,6 +1232,165 @@ bool build_wide_scene(
     return true;
 }
 
+bool build_flat_scene(const WideScene& ws, const uint32_t* indices, const ptgpu_float3* pos,
+                      const ptgpu_tlas_instance* instances, size_t n_static,
+                      uint32_t node_base, uint32_t tri_base, FlatScene& out, std::string& err)
+{
+    const auto t_begin = std::chrono::steady_clock::now();
+    out = FlatScene();
+    unsigned threads = std::thread::hardware_concurrency();
+    if(const char* e = getenv("PTGPU_BUILD_THREADS")) threads = (unsigned)atoi(e);
+    threads = std::max(1u, std::min(threads, 64u));
+
+    // 1. flat triangle numbering: instance i owns [first_tri[i], first_tri[i + 1])
+    std::vector<size_t> first_tri(n_static + 1, 0);
+    for(size_t i = 0; i < n_static; ++i)
+        first_tri[i + 1] = first_tri[i] + ws.blas_info[ws.instances[i].blas].mesh.triangle_count;
+    const size_t n_tris = first_tri[n_static];
+    if(n_tris == 0) { err = "flat scene: no triangles"; return false; }
+    if(n_tris >= 0x7FFFFFFFull || (size_t)tri_base + n_tris >= 0x7FFFFFFFull) { err = "flat scene: too many triangles"; return false; }
+    // world-space vertex k of triangle t of instance i (the arithmetic of mul_m4v4 on a point, math.hh:230-240)
+    auto world_vertex = [&](size_t i, uint32_t t, int k, float v[3]) {
+        const ptgpu_mesh& m = ws.blas_info[ws.instances[i].blas].mesh;
+        const ptgpu_float3& p = pos[m.base_vertex_offset + indices[m.index_offset + 3 * (size_t)t + k]];
+        const ptgpu_float4* c = instances[i].transform.r;
+        v[0] = c[0].x * p.x + c[1].x * p.y + c[2].x * p.z + c[3].x;
+        v[1] = c[0].y * p.x + c[1].y * p.y + c[2].y * p.z + c[3].y;
+        v[2] = c[0].z * p.x + c[1].z * p.y + c[2].z * p.z + c[3].z;
+    };
+    std::vector<uint8_t> mirrored(n_static, 0);   // a reflecting transform turns front faces into back faces
+    for(size_t i = 0; i < n_static; ++i)
+    {
+        const ptgpu_float4* c = instances[i].transform.r;
+        const double det = (double)c[0].x * ((double)c[1].y * c[2].z - (double)c[1].z * c[2].y)
+                         - (double)c[1].x * ((double)c[0].y * c[2].z - (double)c[0].z * c[2].y)
+                         + (double)c[2].x * ((double)c[0].y * c[1].z - (double)c[0].z * c[1].y);
+        mirrored[i] = det < 0.0;
+    }
+    std::vector<Prim> prims(n_tris);
+    parallel_for(n_static, threads, [&](size_t i) {
+        const uint32_t count = ws.blas_info[ws.instances[i].blas].mesh.triangle_count;
+        for(uint32_t t = 0; t < count; ++t)
+        {
+            Prim& pr = prims[first_tri[i] + t];
+            pr.box.reset(); pr.id = (uint32_t)(first_tri[i] + t);
+            for(int k = 0; k < 3; ++k)
+            {
+                float v[3]; world_vertex(i, t, k, v);
+                for(int a = 0; a < 3; ++a) { pr.box.lo[a] = std::min(pr.box.lo[a], v[a]); pr.box.hi[a] = std::max(pr.box.hi[a], v[a]); }
+            }
+        }
+    });
+
+    // 2. top-down into ranges
+    FlatTop top;
+    top.nodes.emplace_back();
+    split_top(prims, 0, n_tris, top, 0, threads > 1);
+    const size_t n_ranges = top.ranges.size();
+
+    // 3. every range: SAH tree -> optimal 8-wide collapse -> compressed nodes + world-space triangles
+    struct Sub { std::vector<float4> nodes, tris; uint32_t depth = 0; std::string err; };
+    std::vector<Sub> subs(n_ranges);
+    parallel_for(n_ranges, threads, [&](size_t r) {
+        Sub& sub = subs[r];
+        const FlatRange fr = top.ranges[r];
+        std::vector<TNode> tree(1);
+        tree.reserve(2 * (fr.end - fr.begin));
+        build_sah(prims, fr.begin, fr.end, tree, 0, 256);
+        sub.tris.reserve(3 * (fr.end - fr.begin));
+        auto emit_leaf = [&](const std::vector<uint32_t>& ids) -> uint32_t {
+            const uint32_t first = (uint32_t)(sub.tris.size() / 3);
+            for(uint32_t id : ids)
+            {
+                const size_t i = (size_t)(std::upper_bound(first_tri.begin(), first_tri.end(), (size_t)id) - first_tri.begin()) - 1;
+                const uint32_t t = (uint32_t)(id - first_tri[i]);
+                for(int k = 0; k < 3; ++k)
+                {
+                    float v[3]; world_vertex(i, t, k, v);
+                    // .w: vertex 0 = primitive id in its mesh, vertex 1 = instance | mirrored << 31
+                    const uint32_t w = k == 0 ? t : k == 1 ? ((uint32_t)i | (mirrored[i] ? 0x80000000u : 0u)) : 0u;
+                    sub.tris.push_back(make_float4(v[0], v[1], v[2], u2f(w)));
+                }
+            }
+            return first;
+        };
+        uint32_t root = build_cw_tree(tree, CW_LEAF_MAX, sub.nodes, emit_leaf, sub.depth, sub.err);
+        if(root != 0u && sub.err.empty()) sub.err = "subtree root is not node 0";
+    });
+    for(const Sub& sub : subs) if(!sub.err.empty()) { err = "flat scene: " + sub.err; return false; }
+
+    // 4. top tree over the ranges; its leaves are placeholders for the subtree roots
+    std::vector<float4> top_nodes;
+    std::vector<std::pair<uint32_t, int>> stubs;
+    uint32_t top_depth = 0;
+    if(n_ranges > 1)
+    {
+        std::vector<TNode> ttree(top.nodes.begin(), top.nodes.end());
+        std::vector<W8Node> w8;
+        OptimalCollapser opt(w8);
+        const int root = opt.build(ttree);
+        const size_t n_w8 = w8.size();
+        for(size_t n = 0; n < n_w8; ++n)
+            for(size_t c = 0; c < w8[n].ch.size(); ++c)
+                if(w8[n].ch[c].inner < 0)
+                {
+                    W8Node stub; stub.box = w8[n].ch[c].box; stub.stub = (int)w8[n].ch[c].leaves[0];
+                    w8[n].ch[c].leaves.clear();
+                    w8[n].ch[c].inner = (int)w8.size();
+                    w8.push_back(std::move(stub));
+                }
+        std::function<uint32_t(const std::vector<uint32_t>&)> no_leaf = [](const std::vector<uint32_t>&) -> uint32_t { return 0u; };
+        CwEmitter em{w8, top_nodes, no_leaf};
+        top_nodes.resize(5);
+        top_depth = em.emit(root, 0u);
+        if(!em.err.empty()) { err = "flat scene, top tree: " + em.err; return false; }
+        cw_breadth_first(top_nodes, (uint32_t)(top_nodes.size() / 5), em.stubs, stubs);
+        if(stubs.size() != n_ranges) { err = "flat scene: top tree lost a range"; return false; }
+    }
+
+    // 5. concatenate: [top nodes | subtree 0 | subtree 1 | ...], indices relocated to the device arrays
+    const uint32_t n_top = (uint32_t)(top_nodes.size() / 5);
+    std::vector<uint32_t> node_off(n_ranges), tri_off(n_ranges);
+    size_t n_nodes = n_top, n_t = 0;
+    for(size_t r = 0; r < n_ranges; ++r)
+    {
+        node_off[r] = (uint32_t)n_nodes; tri_off[r] = (uint32_t)n_t;
+        n_nodes += subs[r].nodes.size() / 5; n_t += subs[r].tris.size() / 3;
+        out.depth = std::max(out.depth, subs[r].depth);
+    }
+    if(n_t != n_tris) { err = "flat scene: triangle count mismatch"; return false; }
+    if((size_t)node_base + n_nodes >= 0x7FFFFFFFull) { err = "flat scene: too many nodes"; return false; }
+    out.depth += top_depth;
+    out.n_top = n_top;
+    out.nodes.resize(5 * n_nodes);
+    out.tris.resize(3 * n_tris);
+    parallel_for(n_ranges, threads, [&](size_t r) {
+        Sub& sub = subs[r];
+        const size_t cnt = sub.nodes.size() / 5;
+        for(size_t n = 0; n < cnt; ++n)
+        {
+            float4* o = &out.nodes[5 * (node_off[r] + n)];
+            for(int k = 0; k < 5; ++k) o[k] = sub.nodes[5 * n + k];
+            o[1].x = u2f(f2u(o[1].x) + node_base + node_off[r]);
+            o[1].y = u2f(f2u(o[1].y) + tri_base + tri_off[r]);
+        }
+        std::copy(sub.tris.begin(), sub.tris.end(), out.tris.begin() + 3 * (size_t)tri_off[r]);
+        sub.nodes = std::vector<float4>(); sub.tris = std::vector<float4>();
+    });
+    for(uint32_t n = 0; n < n_top; ++n)
+    {
+        for(int k = 0; k < 5; ++k) out.nodes[5 * (size_t)n + k] = top_nodes[5 * (size_t)n + k];
+        out.nodes[5 * (size_t)n + 1].x = u2f(f2u(top_nodes[5 * (size_t)n + 1].x) + node_base);
+    }
+    for(const auto& sb : stubs)   // the slot the top tree reserved for a subtree root gets a copy of that root
+        for(int k = 0; k < 5; ++k) out.nodes[5 * (size_t)sb.first + k] = out.nodes[5 * (size_t)node_off[sb.second] + k];
+    const TNode& rootn = top.nodes[0];
+    for(int a = 0; a < 3; ++a) { out.lo[a] = rootn.box.lo[a]; out.hi[a] = rootn.box.hi[a]; }
+    out.n_tris = n_tris;
+    out.build_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count();
+    return true;
+}
+
 // Structural check of a flattened scene, used by the CPU test-suite: every triangle of every BLAS is
 // reachable exactly once, child boxes enclose what is below them, every static instance is a TLAS
 // leaf exactly once. Returns the number of violations.
@@ -1280,6 +1552,75 @@ uint64_t verify_wide_scene(const WideScene& ws, size_t n_static, std::string& er
         if(ws.cw_world_inst < n_static) seen[ws.cw_world_inst]++; // not a TLAS leaf: every query starts inside it
         for(uint32_t c : seen) if(c != 1) { fail("compressed TLAS: instance missing or duplicated"); break; }
     }
+    return bad;
+}
+
+// Structural check of the flat static scene (CPU tests): every triangle is a leaf exactly once, every
+// vertex lies inside its quantised leaf box and inside the slot boxes of all its ancestors.
+uint64_t verify_flat_scene(const FlatScene& fs, uint32_t node_base, uint32_t tri_base, std::string& err)
+{
+    uint64_t bad = 0;
+    auto fail = [&](const std::string& m) { if(bad++ == 0) err = m; };
+    const size_t n_nodes = fs.nodes.size() / 5, n_tris = fs.tris.size() / 3;
+    std::vector<uint8_t> seen(n_tris, 0);
+    struct Todo { uint32_t node; Box box; bool has_box; uint32_t depth; };
+    std::vector<Todo> todo{{0u, Box(), false, 1u}};
+    uint32_t deepest = 0;
+    while(!todo.empty())
+    {
+        Todo t = todo.back(); todo.pop_back();
+        if(t.node >= n_nodes) { fail("flat: child index outside the array"); continue; }
+        deepest = std::max(deepest, t.depth);
+        const float4* n = &fs.nodes[5 * (size_t)t.node];
+        const uint32_t ew = f2u(n[0].w);
+        const float sc[3] = {std::ldexp(1.0f, (int)(int8_t)(ew & 0xFF)), std::ldexp(1.0f, (int)(int8_t)((ew >> 8) & 0xFF)), std::ldexp(1.0f, (int)(int8_t)((ew >> 16) & 0xFF))};
+        const float p[3] = {n[0].x, n[0].y, n[0].z};
+        const uint32_t imask = ew >> 24, child_base = f2u(n[1].x) - node_base, tri_first = f2u(n[1].y) - tri_base;
+        const uint32_t metaw[2] = {f2u(n[1].z), f2u(n[1].w)};
+        const uint32_t q[6][2] = {{f2u(n[2].x), f2u(n[2].y)}, {f2u(n[2].z), f2u(n[2].w)}, {f2u(n[3].x), f2u(n[3].y)},
+                                  {f2u(n[3].z), f2u(n[3].w)}, {f2u(n[4].x), f2u(n[4].y)}, {f2u(n[4].z), f2u(n[4].w)}};
+        uint32_t inner_rank = 0;
+        for(int s = 0; s < 8; ++s)
+        {
+            const uint32_t meta = (metaw[s >> 2] >> (8 * (s & 3))) & 0xFF;
+            bool padding = meta == 0;
+            for(int a = 0; a < 3; ++a)
+                if(((q[a][s >> 2] >> (8 * (s & 3))) & 0xFF) > ((q[3 + a][s >> 2] >> (8 * (s & 3))) & 0xFF)) padding = true;
+            if(padding) { if(imask & (1u << s)) fail("flat: imask set on an empty slot"); continue; }
+            Box cb;
+            for(int a = 0; a < 3; ++a)
+            {
+                cb.lo[a] = p[a] + (float)((q[a][s >> 2] >> (8 * (s & 3))) & 0xFF) * sc[a];
+                cb.hi[a] = p[a] + (float)((q[3 + a][s >> 2] >> (8 * (s & 3))) & 0xFF) * sc[a];
+            }
+            if((imask >> s) & 1u)
+            {
+                Box nb = cb;
+                if(t.has_box) for(int a = 0; a < 3; ++a) { nb.lo[a] = std::max(nb.lo[a], t.box.lo[a]); nb.hi[a] = std::min(nb.hi[a], t.box.hi[a]); }
+                todo.push_back({child_base + inner_rank, nb, true, t.depth + 1});
+                inner_rank++;
+                continue;
+            }
+            const uint32_t idx = tri_first + (meta & 0x1F);
+            if((meta >> 5) != 1u) { fail("flat: leaf child with more than one triangle"); continue; }
+            if(idx >= n_tris) { fail("flat: triangle index outside the array"); continue; }
+            if(seen[idx]++) fail("flat: triangle reachable twice");
+            const float4* v = &fs.tris[3 * (size_t)idx];
+            for(int c = 0; c < 3; ++c)
+            {
+                const float pp[3] = {v[c].x, v[c].y, v[c].z};
+                for(int a = 0; a < 3; ++a)
+                {
+                    if(pp[a] < cb.lo[a] || pp[a] > cb.hi[a]) fail("flat: triangle vertex outside its quantised leaf box");
+                    if(t.has_box && (pp[a] < t.box.lo[a] || pp[a] > t.box.hi[a])) fail("flat: triangle vertex outside an ancestor's slot box");
+                }
+            }
+        }
+    }
+    size_t missing = 0;
+    for(uint8_t c : seen) if(c != 1) missing++;
+    if(missing) fail("flat: " + std::to_string(missing) + " triangles missing or duplicated");
+    if(deepest > fs.depth) fail("flat: depth " + std::to_string(deepest) + " exceeds the recorded " + std::to_string(fs.depth));
     return bad;
 }
 

@@ -46,6 +46,19 @@ struct WideScene
     bool from_meshes = false;           // BLASes built from triangles (ptgpu_upload_meshes), not recovered
 };
 
+// The static instances without instancing: one compressed 8-wide BVH over their world-space triangles
+// (bvh_wide.cu, "flat static scene"). Node and triangle indices are already relocated by the bases the
+// caller passed, so the arrays can be appended to the device copies of cw_nodes / cw_tris.
+struct FlatScene
+{
+    std::vector<float4> nodes;          // 5 per node; node 0 = root; [0, n_top) = the top tree, breadth-first
+    std::vector<float4> tris;           // 3 per triangle: world-space vertices; v0.w = primitive id, v1.w = instance | mirrored << 31
+    uint32_t depth = 0, n_top = 0;
+    size_t n_tris = 0;
+    float lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
+    double build_seconds = 0.0;
+};
+
 constexpr int CW_WIDTH = 8;             // children per node
 constexpr int CW_LEAF_MAX = 1;          // triangles per leaf child (the encoding allows 3; measured 1: 245 ms, 2: 251, 3: 255 on frame 520)
 #ifndef CW_WORLD_START
@@ -67,6 +80,12 @@ bool build_wide_scene(
     const ptgpu_tlas_instance* instances, size_t n_static,
     WideScene& out, std::string& err,
     const ptgpu_mesh* meshes = nullptr, size_t n_meshes = 0);  // nodes == nullptr: build every BLAS from `meshes`
+
+bool build_flat_scene(const WideScene& ws, const uint32_t* indices, const ptgpu_float3* pos,
+                      const ptgpu_tlas_instance* instances, size_t n_static,
+                      uint32_t node_base, uint32_t tri_base, FlatScene& out, std::string& err);
+
+uint64_t verify_flat_scene(const FlatScene& fs, uint32_t node_base, uint32_t tri_base, std::string& err);
 
 // Fills the traversal record of one instance (static or per-frame). False if its BLAS is unknown.
 bool make_wide_instance(const WideScene& ws, const ptgpu_tlas_instance& inst, uint32_t ref_index, WideInstance& out);

@@ -90,21 +90,10 @@ PT_D void cw_set_space(CwState& st, v3 o, v3 d)
     st.oct_inv4 = oct * 0x01010101u;
 }
 
-// Byte j of w as a float. I2F.U8 runs on the XU pipe (61 % busy in wf_trace_cw, 48 conversions per
-// node), so an exact ALU+FMA-pipe form was tried: PRMT builds 2^23 + b, one FADD removes the 2^23.
-// It is slower (CW_CVT 1: all 48 that way, +6 % frame time; 2: the near planes only, +1.4 %): the
-// kernel is bound by issue slots, not by the XU pipe, and the form costs one more instruction per byte.
-#ifndef CW_CVT
-#define CW_CVT 0
-#endif
-PT_D float u8f_xu(uint32_t w, int j) { return (float)((w >> (8 * j)) & 0xFFu); }
-PT_D float u8f_alu(uint32_t w, int j)
-{
-    return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7650u | (uint32_t)j)) - 8388608.0f;
-}
-// near-plane bytes and far-plane bytes may use different pipes (CW_CVT 2: near on ALU+FMA, far on XU)
-PT_D float u8f_near(uint32_t w, int j) { return CW_CVT >= 1 ? u8f_alu(w, j) : u8f_xu(w, j); }
-PT_D float u8f_far(uint32_t w, int j) { return CW_CVT == 1 ? u8f_alu(w, j) : u8f_xu(w, j); }
+// Byte j of w as a float: I2F.U8 (XU pipe). An exact ALU+FMA-pipe form (PRMT builds 2^23 + b, one FADD
+// removes the 2^23) measured 1.4-6 % slower: the kernel is bound by issue slots, not by the XU pipe, and that
+// form costs one more instruction per byte (profiles/r01_trace_kernel_history.md).
+PT_D float u8f(uint32_t w, int j) { return (float)((w >> (8 * j)) & 0xFFu); }
 
 // Box test of the eight children of one node; fills the node group (inner children hit) and the
 // leaf group (leaf payloads whose box was hit).
@@ -133,9 +122,6 @@ PT_D void cw_intersect_node(const float4* __restrict__ nodes, uint32_t node_inde
         const uint32_t is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
         const uint32_t inner_mask4 = sign_extend_s8x4(is_inner4 << 3);
         const uint32_t bit_index4 = (meta4 ^ (st.oct_inv4 & inner_mask4)) & 0x1F1F1F1Fu;
-#if !CW_PAD_EMPTY
-        const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
-#endif
         const uint32_t qlx = __float_as_uint(half ? n2.y : n2.x), qly = __float_as_uint(half ? n2.w : n2.z);
         const uint32_t qlz = __float_as_uint(half ? n3.y : n3.x), qhx = __float_as_uint(half ? n3.w : n3.z);
         const uint32_t qhy = __float_as_uint(half ? n4.y : n4.x), qhz = __float_as_uint(half ? n4.w : n4.z);
@@ -145,18 +131,13 @@ PT_D void cw_intersect_node(const float4* __restrict__ nodes, uint32_t node_inde
         #pragma unroll
         for(int j = 0; j < 4; ++j)
         {
-            const float t0x = fmaf(u8f_near(x_near, j), ax, ox), t1x = fmaf(u8f_far(x_far, j), ax, ox);
-            const float t0y = fmaf(u8f_near(y_near, j), ay, oy), t1y = fmaf(u8f_far(y_far, j), ay, oy);
-            const float t0z = fmaf(u8f_near(z_near, j), az, oz), t1z = fmaf(u8f_far(z_far, j), az, oz);
+            const float t0x = fmaf(u8f(x_near, j), ax, ox), t1x = fmaf(u8f(x_far, j), ax, ox);
+            const float t0y = fmaf(u8f(y_near, j), ay, oy), t1y = fmaf(u8f(y_far, j), ay, oy);
+            const float t0z = fmaf(u8f(z_near, j), az, oz), t1z = fmaf(u8f(z_far, j), az, oz);
             const float cmin = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, st.tmin));
             const float cmax = fminf(fminf(t1x, t1y), fminf(t1z, tmax_box));
-#if CW_PAD_EMPTY
             // every slot holds a real child or an inverted box: no validity mask (the shift uses the low 5 bits)
             if(cmin <= cmax) hitmask |= 1u << ((bit_index4 >> (8 * j)) & 31u);
-#else
-            if(cmin <= cmax)
-                hitmask |= ((child_bits4 >> (8 * j)) & 0xFFu) << ((bit_index4 >> (8 * j)) & 0xFFu);
-#endif
         }
     }
     ngroup.x = __float_as_uint(n1.x);
@@ -165,8 +146,13 @@ PT_D void cw_intersect_node(const float4* __restrict__ nodes, uint32_t node_inde
     tgroup.y = hitmask & 0x00FFFFFFu;
 }
 
+// hit.inst of a world-space query phase: the instance comes from the triangle record
+#define CW_FLAT_INST 0xFFFFFFFEu
+
 // Query start: the subframe's dynamic instances (world-box test) go on the stack as one instance
-// group, then the static TLAS root is the first node group.
+// group. Flat static scene: the query then starts IN the static world (its triangles are stored in world
+// space: no transform, no entry step), the dynamic group waits under an exit marker. Otherwise the static
+// TLAS root is the first node group.
 // PARKED: the caller's exit protocol keeps the world-space ray constants under the exit marker
 // (wf_trace_cw_kernel); otherwise the marker alone (cw_pop_phase recomputes them).
 template<bool PARKED, class Stack>
@@ -188,25 +174,24 @@ PT_D void cw_begin(const Scene& sc, CwState& st, Stack& stack, uint32_t subframe
     }
     if(mask) stack.set(st.sp++, make_uint2(0x80000000u, mask));
     st.tgroup = make_uint2(0u, 0u);
-    if(sc.cw_world_inst == 0xFFFFFFFFu)
+    if(sc.flat_root == 0xFFFFFFFFu)
     {
         st.ngroup = make_uint2(sc.cw_tlas_root, 0x80000000u);
         return;
     }
-    // The query starts INSIDE the world-space instance (identity transform: the terrain, 28 % of all
-    // instance entries when it was a TLAS leaf): no transform, no entry step, and its hit shortens the
-    // ray before the TLAS is walked. The TLAS root group waits on the stack under the exit marker.
-    stack.set(st.sp++, make_uint2(sc.cw_tlas_root, 0x80000000u));
-    if(PARKED)
+    if(mask)
     {
-        stack.set(st.sp++, make_uint2(__float_as_uint(st.idir.x), __float_as_uint(st.idir.y)));
-        stack.set(st.sp++, make_uint2(__float_as_uint(st.idir.z), (st.oct_inv4 & 0xFFu) | (st.sign_bits << 8)));
+        if(PARKED)
+        {
+            stack.set(st.sp++, make_uint2(__float_as_uint(st.idir.x), __float_as_uint(st.idir.y)));
+            stack.set(st.sp++, make_uint2(__float_as_uint(st.idir.z), (st.oct_inv4 & 0xFFu) | (st.sign_bits << 8)));
+        }
+        stack.set(st.sp++, make_uint2(CW_MARK_X, 0u));
     }
-    stack.set(st.sp++, make_uint2(CW_MARK_X, 0u));
     tri_preprocess(rd, st.axis, st.S);
     st.in_blas = true;
-    st.cur_inst = sc.cw_world_inst;
-    st.ngroup = make_uint2(sc.cw_world_root, 0x80000000u);
+    st.cur_inst = CW_FLAT_INST;
+    st.ngroup = make_uint2(sc.flat_root, 0x80000000u);
 }
 
 PT_D uint32_t cw_decode_instance(const Scene& sc, const CwState& st, uint32_t base, uint32_t bit)
@@ -254,12 +239,16 @@ PT_D void cw_test_triangle(const Scene& sc, CwState& st, uint32_t tri)
     // tests triangles in an order that depends on warp scheduling, so ties are broken by the smallest
     // (instance, primitive) instead: deterministic and independent of traversal order.
     const uint32_t prim = __float_as_uint(a.w);
+    // world-space triangles of the flat static scene name their instance (and whether its transform mirrors,
+    // which swaps front and back); BLAS triangles belong to the instance the ray is in (their b.w is 0)
+    const uint32_t bw = __float_as_uint(b.w);
+    const uint32_t inst = st.cur_inst == CW_FLAT_INST ? (bw & 0x7FFFFFFFu) : st.cur_inst;
     const bool closer = t < st.tmax;
     const bool tie = st.hit.t >= 0.0f && t == st.hit.t &&
-        (st.cur_inst < st.hit.inst || (st.cur_inst == st.hit.inst && prim < st.hit.prim));
+        (inst < st.hit.inst || (inst == st.hit.inst && prim < st.hit.prim));
     if(ok && t > st.tmin && (closer || tie))
     {
-        st.hit.t = t; st.hit.u = u; st.hit.v = v; st.hit.inst = st.cur_inst; st.hit.prim = prim; st.hit.back_face = bf;
+        st.hit.t = t; st.hit.u = u; st.hit.v = v; st.hit.inst = inst; st.hit.prim = prim; st.hit.back_face = bf != ((bw >> 31) != 0u);
         st.tmax = t;
         if(st.any) { st.sp = 0; st.ngroup.y = 0u; st.tgroup.y = 0u; }
     }

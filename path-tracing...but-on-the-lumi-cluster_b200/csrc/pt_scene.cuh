@@ -3,12 +3,9 @@
 #include "pt_math.cuh"
 #include "pt_shade.cuh"
 
-// Compressed 8-wide nodes: 1 = the empty child slots of a node carry an INVERTED box (lo 255, hi 0: no ray
+// Compressed 8-wide nodes: the empty child slots of a node carry an INVERTED box (lo 255, hi 0: no ray
 // passes the slab test) and the meta byte of one of the node's real children, so the box test needs no
 // per-child validity mask: a child that passes sets bit (1 << its index). Needs one triangle per leaf child.
-#ifndef CW_PAD_EMPTY
-#define CW_PAD_EMPTY 1
-#endif
 
 namespace pt {
 
@@ -106,8 +103,12 @@ struct Scene
     const float4* cwtris;           // 3 float4 per triangle, leaf order; p0.w = primitive id (bits)
     const uint32_t* cw_inst_index;  // TLAS leaf order -> instance index
     uint32_t cw_tlas_root;
-    uint32_t cw_world_inst;         // static instance every query starts in (identity transform), or 0xFFFFFFFF
-    uint32_t cw_world_root;         // its BLAS root in cwnodes
+    // flat static scene (bvh_wide.cu): root of the one BVH over the world-space triangles of all static
+    // instances, in cwnodes / cwtris behind the BLASes; 0xFFFFFFFF = walk the static TLAS + BLASes instead
+    uint32_t flat_root;
+    uint32_t flat_top;              // nodes [flat_root, flat_root + flat_top) are its top levels, breadth-first
+    // ray-sort grid (pt_wave.cuh): cell = (p - key_lo) * key_scale, 32 x 8 x 32 cells over the static scene
+    float key_lo[3], key_scale[3];
     uint32_t n_static;
     uint32_t n_subframes;
     // config

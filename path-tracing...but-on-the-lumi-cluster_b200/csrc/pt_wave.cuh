@@ -59,6 +59,13 @@ struct WaveBuffers
     // primary rays of neighbouring pixels stay together (coherent), sun-ward shadow rays share a
     // direction, bounce rays are incoherent anyway. Entry = slot | WF_SHADOW_BIT.
     uint32_t* q_trace;    // 3 segments of seg_cap entries
+    // Ray sort (wf_sort_*): shade writes a 13-bit key beside every bounce / shadow entry (direction octant
+    // + Morton cell of the origin); one counting-sort pass per segment reorders the entries into q_sorted,
+    // which is what wf_trace_cw then fetches from (the primary segment is already in pixel-tile order).
+    uint32_t* q_key;      // 3 segments of seg_cap keys, parallel to q_trace (the primary segment's are unused)
+    uint32_t* q_sorted;   // 2 segments of seg_cap entries: sorted bounce rays, sorted shadow rays
+    uint32_t* sort_hist;  // 2 x WF_SORT_BINS: per-bin counts, then the running output cursors
+    int32_t sort;         // 0: wf_trace_cw reads q_trace as it was appended
     uint8_t* status;      // per slot: WF_ST_*, written by wf_trace when a closest-hit query ends
     uint32_t* q_far;      // shade queues, filled by wf_classify in slot order
     uint32_t* q_near;
@@ -96,7 +103,8 @@ PT_D void wf_append(uint32_t* q, uint32_t* count, bool pred, uint32_t val)
 // address with per-warp appends). Must be reached by every thread of the block the same number of times;
 // `s_tmp` is WARPS + 1 words of shared memory per call site. Block order = warp order = slot order.
 template<int WARPS>
-PT_D void wf_append_block(uint32_t* q, uint32_t* count, bool pred, uint32_t val, uint32_t* s_tmp)
+PT_D void wf_append_block(uint32_t* q, uint32_t* count, bool pred, uint32_t val, uint32_t* s_tmp,
+                          uint32_t* q_key = nullptr, uint32_t key = 0u)
 {
     const unsigned m = __ballot_sync(0xFFFFFFFFu, pred);
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
@@ -114,9 +122,119 @@ PT_D void wf_append_block(uint32_t* q, uint32_t* count, bool pred, uint32_t val,
     {
         uint32_t base = s_tmp[WARPS];
         for(unsigned k = 0; k < warp; ++k) base += s_tmp[k];
-        q[base + __popc(m & ((1u << lane) - 1u))] = val;
+        const uint32_t pos = base + __popc(m & ((1u << lane) - 1u));
+        q[pos] = val;
+        if(q_key) q_key[pos] = key;
     }
     __syncthreads();
+}
+
+// ---- ray sort ---------------------------------------------------------------------------------------------
+// Bounce rays leave a surface in a random direction of the hemisphere and, from the second bounce on,
+// from anywhere in the scene: a warp of 32 consecutive queue entries walked 32 unrelated parts of the BVH
+// (19 of 32 lanes per instruction in wf_trace_cw, 11 in its triangle step). Key: the direction octant — the
+// order the 8-wide nodes store their children in, and what the reference's eight link tables are indexed by
+// (ray_query.hh:135-140) — and the Morton code of the origin's cell in a 32 x 8 x 32 grid over the static
+// scene. Shadow rays all point at the sun (4 degree cone), so their key spends all 13 bits on the origin.
+constexpr uint32_t WF_SORT_BINS = 8192;      // 13-bit keys
+constexpr uint32_t WF_SORT_CHUNK = 32768;    // entries per block iteration
+constexpr int WF_SORT_THREADS = 512;
+
+PT_D uint32_t spread_bits(uint32_t v)
+{   // bit i of v -> bit 2i
+    v = (v | (v << 4)) & 0x0F0F0F0Fu;
+    v = (v | (v << 2)) & 0x33333333u;
+    v = (v | (v << 1)) & 0x55555555u;
+    return v;
+}
+PT_D uint32_t sort_key(const Scene& sc, v3 o, v3 d, bool shadow)
+{
+    const uint32_t cx = (uint32_t)fminf(fmaxf((o.x - sc.key_lo[0]) * sc.key_scale[0], 0.0f), 31.0f);
+    const uint32_t cy = (uint32_t)fminf(fmaxf((o.y - sc.key_lo[1]) * sc.key_scale[1], 0.0f), 7.0f);
+    const uint32_t cz = (uint32_t)fminf(fmaxf((o.z - sc.key_lo[2]) * sc.key_scale[2], 0.0f), 31.0f);
+    if(shadow) return ((spread_bits(cx) | (spread_bits(cz) << 1)) << 3) | cy;
+    const uint32_t oct = (d.x < 0.0f ? 0u : 4u) | (d.y < 0.0f ? 0u : 2u) | (d.z < 0.0f ? 0u : 1u);
+    return ((((spread_bits(cx >> 1) | (spread_bits(cz >> 1) << 1)) << 2) | (cy >> 1)) << 3) | oct;
+}
+
+// pass 1: per-bin counts of both segments (blockIdx.y: 0 bounce, 1 shadow), one shared-memory histogram
+// per block, one global atomic per non-empty bin and block
+__global__ void __launch_bounds__(WF_SORT_THREADS)
+wf_sort_count_kernel(WaveBuffers wb)
+{
+    __shared__ uint32_t h[WF_SORT_BINS];
+    const int seg = blockIdx.y ? WF_SEG_SHADOW : WF_SEG_BOUNCE;
+    const uint32_t n = wb.cnt->n_seg[seg];
+    if((size_t)blockIdx.x * WF_SORT_CHUNK >= n) return;
+    const uint32_t* keys = wb.q_key + seg * (size_t)wb.seg_cap;
+    for(uint32_t b = threadIdx.x; b < WF_SORT_BINS; b += WF_SORT_THREADS) h[b] = 0u;
+    __syncthreads();
+    for(size_t c = blockIdx.x; c * WF_SORT_CHUNK < n; c += gridDim.x)
+    {
+        const uint32_t begin = (uint32_t)(c * WF_SORT_CHUNK), end = min(n, begin + WF_SORT_CHUNK);
+        for(uint32_t i = begin + threadIdx.x; i < end; i += WF_SORT_THREADS) atomicAdd(&h[keys[i] & (WF_SORT_BINS - 1u)], 1u);
+    }
+    __syncthreads();
+    uint32_t* hist = wb.sort_hist + blockIdx.y * WF_SORT_BINS;
+    for(uint32_t b = threadIdx.x; b < WF_SORT_BINS; b += WF_SORT_THREADS) if(h[b]) atomicAdd(&hist[b], h[b]);
+}
+
+// pass 2: exclusive scan of the bin counts, in place (one block per segment)
+__global__ void __launch_bounds__(1024)
+wf_sort_scan_kernel(WaveBuffers wb)
+{
+    __shared__ uint32_t s_warp[32];
+    uint32_t* hist = wb.sort_hist + blockIdx.x * WF_SORT_BINS;
+    constexpr uint32_t PER = WF_SORT_BINS / 1024;
+    uint32_t v[PER], sum = 0;
+    #pragma unroll
+    for(uint32_t k = 0; k < PER; ++k) { v[k] = hist[threadIdx.x * PER + k]; sum += v[k]; }
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    uint32_t incl = sum;
+    #pragma unroll
+    for(int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o); if(lane >= (unsigned)o) incl += t; }
+    if(lane == 31u) s_warp[warp] = incl;
+    __syncthreads();
+    if(warp == 0)
+    {
+        uint32_t w = s_warp[lane], wi = w;
+        #pragma unroll
+        for(int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, wi, o); if(lane >= (unsigned)o) wi += t; }
+        s_warp[lane] = wi - w;
+    }
+    __syncthreads();
+    uint32_t run = s_warp[warp] + incl - sum;
+    #pragma unroll
+    for(uint32_t k = 0; k < PER; ++k) { hist[threadIdx.x * PER + k] = run; run += v[k]; }
+}
+
+// pass 3: scatter. A block counts its chunk again, claims a run in every bin it touches with one global
+// atomic, and places its entries with shared-memory atomics. The order inside a bin is the order in which
+// blocks claimed their runs — not reproducible, and it need not be: a query's result does not depend on
+// the queue order (ties are broken by ids, pt_cwbvh.cuh), and the shade queues are rebuilt in slot order.
+__global__ void __launch_bounds__(WF_SORT_THREADS)
+wf_sort_scatter_kernel(WaveBuffers wb)
+{
+    __shared__ uint32_t h[WF_SORT_BINS];
+    const int seg = blockIdx.y ? WF_SEG_SHADOW : WF_SEG_BOUNCE;
+    const uint32_t n = wb.cnt->n_seg[seg];
+    const uint32_t* keys = wb.q_key + seg * (size_t)wb.seg_cap;
+    const uint32_t* in = wb.q_trace + seg * (size_t)wb.seg_cap;
+    uint32_t* out = wb.q_sorted + blockIdx.y * (size_t)wb.seg_cap;
+    uint32_t* cursor = wb.sort_hist + blockIdx.y * WF_SORT_BINS;
+    for(size_t c = blockIdx.x; c * WF_SORT_CHUNK < n; c += gridDim.x)
+    {
+        const uint32_t begin = (uint32_t)(c * WF_SORT_CHUNK), end = min(n, begin + WF_SORT_CHUNK);
+        for(uint32_t b = threadIdx.x; b < WF_SORT_BINS; b += WF_SORT_THREADS) h[b] = 0u;
+        __syncthreads();
+        for(uint32_t i = begin + threadIdx.x; i < end; i += WF_SORT_THREADS) atomicAdd(&h[keys[i] & (WF_SORT_BINS - 1u)], 1u);
+        __syncthreads();
+        for(uint32_t b = threadIdx.x; b < WF_SORT_BINS; b += WF_SORT_THREADS) if(h[b]) h[b] = atomicAdd(&cursor[b], h[b]);
+        __syncthreads();
+        for(uint32_t i = begin + threadIdx.x; i < end; i += WF_SORT_THREADS)
+            out[atomicAdd(&h[keys[i] & (WF_SORT_BINS - 1u)], 1u)] = in[i];
+        __syncthreads();
+    }
 }
 
 // ---- init: every slot starts idle; valid ones are queued for their first sample ---------------
@@ -182,192 +300,7 @@ constexpr int WF_TRACE_THREADS = 128;
 #endif
 constexpr int WF_FETCH_CHUNK = WF_FETCH_CHUNK_N;
 
-__global__ void __launch_bounds__(WF_TRACE_THREADS, 6)
-wf_trace_kernel(Scene sc, RenderJob job, WaveBuffers wb)
-{
-    const unsigned lane = threadIdx.x & 31u;
-    const uint32_t n_s0 = wb.cnt->n_seg[0], n_s1 = wb.cnt->n_seg[1], n_s2 = wb.cnt->n_seg[2];
-    const uint32_t n_entries = n_s0 + n_s1 + n_s2;
-
-    // warp-uniform reserve of queue entries [res_base, res_base + res_n)
-    uint32_t res_base = 0, res_n = 0;
-    bool exhausted = false;
-
-    bool active = false;
-    uint32_t slot = 0;
-    bool shadow_ray = false;
-    uint32_t subframe = 0;
-
-    uint32_t stack[WIDE_STACK];
-    int sp = 0;
-    uint32_t cur = PT_EMPTY;
-    v3 ro = mk3(0, 0, 0), rd = mk3(0, 0, 1);
-    v3 o = ro, d = rd, inv = mk3(0, 0, 0), S = mk3(0, 0, 1);
-    int axis = 2;
-    bool in_blas = false;
-    const WideNode* nodes = sc.wtlas;
-    const float4* tris = sc.wtris;
-    uint32_t cur_inst = 0;
-    float tmin = 0.0f, tmax = 0.0f;
-    Hit hit; hit.t = -1.0f; hit.u = hit.v = 0.0f; hit.inst = 0; hit.prim = 0; hit.back_face = false;
-
-    for(;;)
-    {
-        const unsigned act = __ballot_sync(0xFFFFFFFFu, active);
-        // refill when at least job.min_active lanes are idle (or nothing is running)
-        if(__popc(act) <= 32 - job.min_active || act == 0u)
-        {
-            // -- refill idle lanes from the ray queue ------------------------------------------------
-            const unsigned idle = ~act;
-            uint32_t want = (uint32_t)__popc(idle);
-            const uint32_t my_rank = (uint32_t)__popc(idle & ((1u << lane) - 1u));
-            uint32_t entry_index = WF_INVALID;
-            uint32_t served = 0;
-            while(want > served && !(exhausted && res_n == 0u))
-            {
-                if(res_n == 0u)
-                {
-                    uint32_t b = 0;
-                    if(lane == 0) b = atomicAdd(&wb.cnt->cur_trace, (uint32_t)WF_FETCH_CHUNK);
-                    b = __shfl_sync(0xFFFFFFFFu, b, 0);
-                    if(b >= n_entries) { exhausted = true; break; }
-                    res_base = b;
-                    res_n = min((uint32_t)WF_FETCH_CHUNK, n_entries - b);
-                }
-                const uint32_t take = min(res_n, want - served);
-                if(!active && my_rank >= served && my_rank < served + take) entry_index = res_base + (my_rank - served);
-                res_base += take; res_n -= take; served += take;
-            }
-            if(entry_index != WF_INVALID)
-            {
-                // logical index over [bounce | primary | shadow] -> segment position
-                const uint32_t e = entry_index < n_s0 ? __ldg(wb.q_trace + entry_index) :
-                    entry_index - n_s0 < n_s1 ? __ldg(wb.q_trace + wb.seg_cap + (entry_index - n_s0)) :
-                    __ldg(wb.q_trace + 2 * (size_t)wb.seg_cap + (entry_index - n_s0 - n_s1));
-                if(e != WF_INVALID)
-                {
-                    slot = e & ~WF_SHADOW_BIT;
-                    shadow_ray = (e & WF_SHADOW_BIT) != 0u;
-                    const float4 fo = wb.ray_o[slot];
-                    const float4 fd = shadow_ray ? wb.shadow_d[slot] : wb.ray_d[slot];
-                    const int sample = job.s_begin + wb.cursor[slot].x * job.s_stride;
-                    subframe = sample < 0 ? 0u : (uint32_t)sample / (uint32_t)sc.samples_per_subframe;
-                    ro = mk3(fo.x, fo.y, fo.z); rd = mk3(fd.x, fd.y, fd.z);
-                    tmin = fo.w; tmax = PT_MAX_RAY_DIST;
-                    // query start: dynamic instances of the subframe, then the static TLAS root
-                    hit.t = -1.0f; hit.u = 0.0f; hit.v = 0.0f; hit.inst = 0xFFFFFFFFu; hit.prim = 0; hit.back_face = false;
-                    sp = 0;
-                    o = ro; d = rd; inv = safe_inv_dir(rd);
-                    in_blas = false; nodes = sc.wtlas;
-                    const uint2 r = __ldg(sc.dyn_range + subframe);
-                    const uint32_t p = r.x, a = r.y & 0xFFFFFu, len = r.y >> 20;
-                    for(uint32_t i = 0; i < p + len; ++i)
-                    {
-                        const uint32_t id = sc.n_static + (i < p ? i : a + (i - p));
-                        const WideInstance* wi = sc.winst + id;
-                        if(box_hit(__ldg(&wi->lo), __ldg(&wi->hi), o, inv, tmin, tmax))
-                            stack[sp++] = 0x80000000u | id;
-                    }
-                    cur = 0;
-                    active = true;
-                }
-            }
-            if(__ballot_sync(0xFFFFFFFFu, active) == 0u)
-            {
-                if(exhausted && res_n == 0u) break;
-                continue;
-            }
-        }
-        // -- advance: pop / complete (cheap, every lane) ---------------------------------------------
-        if(active && cur == PT_EMPTY)
-        {
-            if(sp == 0)
-            {   // query complete: write the result
-                active = false;
-                if(shadow_ray) wb.visible[slot] = hit.t < 0.0f ? 1u : 0u;
-                else
-                {
-                    wb.hit[slot] = make_float4(hit.t, hit.u, hit.v, __uint_as_float(hit.inst));
-                    wb.hit_prim[slot] = hit.prim | (hit.back_face ? 0x80000000u : 0u);
-                    wb.status[slot] = (hit.t > 0.0f && hit.t < 1e3f) ? WF_ST_NEAR : WF_ST_FAR;
-                }
-            }
-            else cur = stack[--sp];
-        }
-
-        // -- phase vote: run ONE code block per iteration, the one most lanes are waiting for. ncu on
-        //    the unvoted loop: triangle tests ran with 2.4 of 32 lanes and were 45% of all issued
-        //    instructions; lanes now wait at a leaf until the leaf block is elected.
-        const bool w_inner = active && !(cur & 0x80000000u);
-        const bool w_tri = active && (cur & 0x80000000u) && in_blas && cur != PT_EXIT_MARK;
-        const bool w_xform = active && (cur & 0x80000000u) && (!in_blas || cur == PT_EXIT_MARK);
-        const int n_inner = __popc(__ballot_sync(0xFFFFFFFFu, w_inner));
-        const int n_tri = __popc(__ballot_sync(0xFFFFFFFFu, w_tri));
-        const int n_xform = __popc(__ballot_sync(0xFFFFFFFFu, w_xform));
-        if(n_inner >= n_tri && n_inner >= n_xform)
-        {
-            if(w_inner)
-            {
-                uint32_t key[4]; uint4 child;
-                test4(nodes + cur, o, inv, tmin, tmax, key, child);
-                cswap(key[0], key[1]); cswap(key[2], key[3]); cswap(key[0], key[2]); cswap(key[1], key[3]); cswap(key[1], key[2]);
-                if(key[3] != PT_EMPTY) stack[sp++] = pick_child(child, key[3] & 3u);
-                if(key[2] != PT_EMPTY) stack[sp++] = pick_child(child, key[2] & 3u);
-                if(key[1] != PT_EMPTY) stack[sp++] = pick_child(child, key[1] & 3u);
-                cur = key[0] != PT_EMPTY ? pick_child(child, key[0] & 3u) : PT_EMPTY;
-            }
-        }
-        else if(n_tri >= n_xform)
-        {
-            if(w_tri)
-            {   // one triangle of the leaf per election (ray_query_test_triangle, ray_query.hh:225-246)
-                const uint32_t first = cur & 0x07FFFFFFu, more = (cur >> 27) & 0xFu;
-                const float4* tp = tris + 3 * (size_t)first;
-                const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
-                cur = more ? (0x80000000u | ((more - 1u) << 27) | (first + 1u)) : PT_EMPTY;
-                float u, v, t; bool bf;
-                bool ok = tri_intersect(o, axis, S, mk3(a), mk3(b), mk3(c), u, v, t, bf);
-                if(ok && t < tmax && t > tmin)
-                {
-                    hit.t = t; hit.u = u; hit.v = v; hit.inst = cur_inst; hit.prim = __float_as_uint(a.w); hit.back_face = bf;
-                    tmax = t;
-                    if(shadow_ray) { sp = 0; cur = PT_EMPTY; } // any hit ends a shadow query
-                }
-            }
-        }
-        else if(w_xform)
-        {
-            if(cur == PT_EXIT_MARK)
-            {   // BLAS finished: back to world space
-                in_blas = false; nodes = sc.wtlas; o = ro; d = rd; inv = safe_inv_dir(rd);
-                cur = PT_EMPTY;
-            }
-            else
-            {   // TLAS leaf: enter the instance (ray_query_enter_blas, ray_query.hh:153-182)
-                cur_inst = cur & 0x7FFFFFFFu;
-                const WideInstance* wi = sc.winst + cur_inst;
-                const float4 r0 = __ldg(&wi->inv0), r1 = __ldg(&wi->inv1), r2 = __ldg(&wi->inv2);
-                const uint32_t b = __ldg(&wi->blas);
-                o = mk3(r0.x * ro.x + r0.y * ro.y + r0.z * ro.z + r0.w,
-                        r1.x * ro.x + r1.y * ro.y + r1.z * ro.z + r1.w,
-                        r2.x * ro.x + r2.y * ro.y + r2.z * ro.z + r2.w);
-                d = mk3(r0.x * rd.x + r0.y * rd.y + r0.z * rd.z,
-                        r1.x * rd.x + r1.y * rd.y + r1.z * rd.z,
-                        r2.x * rd.x + r2.y * rd.y + r2.z * rd.z);
-                inv = safe_inv_dir(d);
-                tri_preprocess(d, axis, S);
-                const uint2 bo = __ldg(reinterpret_cast<const uint2*>(sc.wblas + b));
-                nodes = sc.wnodes + bo.x;
-                tris = sc.wtris + 3 * (size_t)bo.y;
-                in_blas = true;
-                stack[sp++] = PT_EXIT_MARK;
-                cur = 0;
-            }
-        }
-    }
-}
-
-// ---- trace on the compressed 8-wide BVH (pt_cwbvh.cuh): same queue protocol as wf_trace_kernel ------
+// ---- trace on the compressed 8-wide BVH (pt_cwbvh.cuh) ---------------------------------------------
 //
 // Scheduling inside a warp (each decision backed by an ncu source-level profile, profiles/):
 //   * one code block per iteration, elected by ballot: NODE (box tests of one 8-wide node), TRI (one
@@ -378,9 +311,6 @@ wf_trace_kernel(Scene sc, RenderJob job, WaveBuffers wb)
 //   * leaving an instance is free: the world-space ray constants are parked under the exit marker;
 //   * a lane whose query ends takes the next ray from the global queue (refill when >= min_active
 //     lanes are idle), closest-hit and shadow rays alike.
-#ifndef WF_INSTANCES_FIRST
-#define WF_INSTANCES_FIRST 0
-#endif
 #ifndef CW_PEND_N
 #define CW_PEND_N 4
 #endif
@@ -437,10 +367,13 @@ wf_trace_cw_kernel(Scene sc, RenderJob job, WaveBuffers wb)
             }
             if(entry_index != WF_INVALID)
             {
-                // logical index over [bounce | primary | shadow] -> segment position
-                const uint32_t e = entry_index < n_s0 ? __ldg(wb.q_trace + entry_index) :
+                // logical index over [bounce | primary | shadow] -> segment position (sorted copies of the
+                // bounce and shadow segments when the ray sort is on)
+                const uint32_t* seg_bounce = wb.sort ? wb.q_sorted : wb.q_trace;
+                const uint32_t* seg_shadow = wb.sort ? wb.q_sorted + wb.seg_cap : wb.q_trace + 2 * (size_t)wb.seg_cap;
+                const uint32_t e = entry_index < n_s0 ? __ldg(seg_bounce + entry_index) :
                     entry_index - n_s0 < n_s1 ? __ldg(wb.q_trace + wb.seg_cap + (entry_index - n_s0)) :
-                    __ldg(wb.q_trace + 2 * (size_t)wb.seg_cap + (entry_index - n_s0 - n_s1));
+                    __ldg(seg_shadow + (entry_index - n_s0 - n_s1));
                 if(e != WF_INVALID)
                 {
                     slot = e & ~WF_SHADOW_BIT;
@@ -518,11 +451,9 @@ wf_trace_cw_kernel(Scene sc, RenderJob job, WaveBuffers wb)
             if(st.tgroup.y != 0u)
             {
                 if(st.in_blas) { pend[(np++) * WF_TRACE_THREADS] = st.tgroup; st.tgroup.y = 0u; }              // triangles wait for the TRI block
-#if WF_INSTANCES_FIRST
-                else if(st.ngroup.y > 0x00FFFFFFu) { stack.set(st.sp++, st.ngroup); st.ngroup.y = 0u; } // the node's inner children wait below its instances
-#else
-                else if(st.ngroup.y > 0x00FFFFFFu) { stack.set(st.sp++, st.tgroup); st.tgroup.y = 0u; } // instances wait below the TLAS nodes
-#endif
+                // instances wait below the TLAS nodes (entering them first measured 3-4 % slower on forest frames:
+                // entries spread out in time and fewer lanes share an ENTER step)
+                else if(st.ngroup.y > 0x00FFFFFFu) { stack.set(st.sp++, st.tgroup); st.tgroup.y = 0u; }
             }
         };
         auto tri_step = [&]() {
@@ -737,6 +668,7 @@ wf_shade_kernel(Scene sc, RenderJob job, WaveBuffers wb)
     {
         const uint32_t slot = i < n ? q[i] : WF_INVALID;
         bool push_ext = false, push_shadow = false, push_new = false;
+        uint32_t key_ext = 0u, key_shadow = 0u;
         if(slot != WF_INVALID)
         {
             int2 cursor = wb.cursor[slot];
@@ -827,10 +759,18 @@ wf_shade_kernel(Scene sc, RenderJob job, WaveBuffers wb)
                 wb.cursor[slot] = cursor;
                 push_ext = true;
                 push_shadow = lit;
+                if(wb.sort)
+                {
+                    key_ext = sort_key(sc, info.pos, bounce_d, false);
+                    key_shadow = sort_key(sc, info.pos, light_dir, true);
+                }
             }
         }
-        wf_append_block<4>(wb.q_trace + WF_SEG_SHADOW * (size_t)wb.seg_cap, &wb.cnt->n_seg[WF_SEG_SHADOW], push_shadow, slot | WF_SHADOW_BIT, s_tmp[0]);
-        wf_append_block<4>(wb.q_trace + WF_SEG_BOUNCE * (size_t)wb.seg_cap, &wb.cnt->n_seg[WF_SEG_BOUNCE], push_ext, slot, s_tmp[1]);
+        uint32_t* keys = wb.sort ? wb.q_key : nullptr;
+        wf_append_block<4>(wb.q_trace + WF_SEG_SHADOW * (size_t)wb.seg_cap, &wb.cnt->n_seg[WF_SEG_SHADOW], push_shadow, slot | WF_SHADOW_BIT, s_tmp[0],
+                           keys ? keys + WF_SEG_SHADOW * (size_t)wb.seg_cap : nullptr, key_shadow);
+        wf_append_block<4>(wb.q_trace + WF_SEG_BOUNCE * (size_t)wb.seg_cap, &wb.cnt->n_seg[WF_SEG_BOUNCE], push_ext, slot, s_tmp[1],
+                           keys ? keys + WF_SEG_BOUNCE * (size_t)wb.seg_cap : nullptr, key_ext);
         // n_new is a flag (wf_generate only asks whether it is non-zero): a plain store, not an atomic per warp
         if(__any_sync(0xFFFFFFFFu, push_new) && (threadIdx.x & 31u) == 0u) wb.cnt->n_new = 1u;
     }

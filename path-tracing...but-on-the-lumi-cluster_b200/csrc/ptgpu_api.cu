@@ -7,9 +7,14 @@
 #include "pt_cwbvh.cuh"
 #include "bvh_wide.hh"
 
+#include <algorithm>
+#include <cfloat>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -44,6 +49,20 @@ struct DevBuf
     void release() { if(p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
+// The flat static scene takes seconds to build (15.6 M triangles at the shipped scene) and depends only on
+// the uploaded arrays: contexts of one process that upload the same scene (one per GPU in the driver, one
+// per test in the test-suite) share one build.
+uint64_t hash_bytes(uint64_t h, const void* p, size_t n)
+{
+    const uint64_t* w = (const uint64_t*)p;
+    for(size_t i = 0; i < n / 8; ++i) { h ^= w[i]; h *= 0x100000001B3ull; h ^= h >> 29; }
+    const uint8_t* b = (const uint8_t*)p + (n & ~size_t(7));
+    for(size_t i = 0; i < (n & 7); ++i) { h ^= b[i]; h *= 0x100000001B3ull; }
+    return h;
+}
+std::mutex g_flat_mutex;
+std::map<uint64_t, std::shared_ptr<const FlatScene>> g_flat_cache;
+
 } // namespace
 
 struct ptgpu_ctx
@@ -65,6 +84,9 @@ struct ptgpu_ctx
     int max_lanes = 256;                       // wavefront: slots per pixel (power of two)
     size_t pool_budget_bytes = 16ull << 30;    // wavefront: path-state pool budget
     int tri_threshold = 8, xform_threshold = 4, node_threshold = 16, node_burst = 2;
+    int flat = 1;                              // static instances as one world-space BVH (built at upload)
+    int sort = 1;                              // wavefront: bounce and shadow rays sorted by octant + origin cell
+    int top_smem = 0;                          // wavefront: top levels of the flat BVH staged in shared memory
 
     // static scene, reference layout
     DevBuf<float2> ref_nodes;     // 3 per node; static region then per-frame TLAS region
@@ -86,8 +108,13 @@ struct ptgpu_ctx
     DevBuf<WideInstance> winst;     // static + dynamic
     DevBuf<WideNode> wtlas;
     size_t n_wtlas = 0;
-    DevBuf<float4> cwnodes, cwtris;
+    DevBuf<float4> cwnodes, cwtris;   // BLASes + static TLAS, then (flat scene) the world-space BVH of all static instances
     DevBuf<uint32_t> cw_inst_index;
+    bool have_flat = false;
+    uint32_t flat_root = 0xFFFFFFFFu, flat_top = 0, flat_depth = 0;
+    size_t flat_tris = 0, flat_nodes = 0;
+    double flat_build_seconds = 0.0;
+    float key_lo[3] = {0, 0, 0}, key_scale[3] = {0, 0, 0};
 
     // per frame
     DevBuf<RefSubframe> subframes;
@@ -112,7 +139,7 @@ struct ptgpu_ctx
     size_t last_pool_bytes = 0;
     // per-kernel device time of the last wavefront frame (CUDA events on the render stream)
     std::vector<cudaEvent_t> wave_events;
-    double last_trace_us = 0.0, last_shade_us = 0.0;
+    double last_trace_us = 0.0, last_shade_us = 0.0, last_sort_us = 0.0;
     uint64_t last_trace_launches = 0;
     int wave_timed_rounds = 0;
     unsigned long long last_validate_mismatches = 0;
@@ -171,8 +198,9 @@ Scene make_scene(ptgpu_ctx* ctx)
     s.wtlas = ctx->wtlas.p; s.dyn_range = ctx->dyn_range.p;
     s.cwnodes = ctx->cwnodes.p; s.cwtris = ctx->cwtris.p; s.cw_inst_index = ctx->cw_inst_index.p;
     s.cw_tlas_root = ctx->wide_host.cw_tlas_root;
-    s.cw_world_inst = ctx->wide_host.cw_world_inst;
-    s.cw_world_root = s.cw_world_inst != 0xFFFFFFFFu ? ctx->wide_host.instances[s.cw_world_inst].cw_root : 0u;
+    s.flat_root = ctx->flat && ctx->have_flat ? ctx->flat_root : 0xFFFFFFFFu;
+    s.flat_top = ctx->flat_top;
+    for(int a = 0; a < 3; ++a) { s.key_lo[a] = ctx->key_lo[a]; s.key_scale[a] = ctx->key_scale[a]; }
     s.n_static = (uint32_t)ctx->n_static;
     s.n_subframes = (uint32_t)ctx->n_subframes;
     s.width = ctx->cfg.width; s.height = ctx->cfg.height;
@@ -196,14 +224,15 @@ int check_ready(ptgpu_ctx* ctx)
 void wave_timing(ptgpu_ctx* ctx)
 {
     if(ctx->wave_timed_rounds <= 0) return;
-    cudaEventSynchronize(ctx->wave_events[3 * (ctx->wave_timed_rounds - 1) + 2]);
-    ctx->last_trace_us = ctx->last_shade_us = 0.0;
+    cudaEventSynchronize(ctx->wave_events[4 * (ctx->wave_timed_rounds - 1) + 3]);
+    ctx->last_trace_us = ctx->last_shade_us = ctx->last_sort_us = 0.0;
     for(int i = 0; i < ctx->wave_timed_rounds; ++i)
     {
-        float a = 0.f, b = 0.f;
-        cudaEventElapsedTime(&a, ctx->wave_events[3 * i], ctx->wave_events[3 * i + 1]);
-        cudaEventElapsedTime(&b, ctx->wave_events[3 * i + 1], ctx->wave_events[3 * i + 2]);
-        ctx->last_trace_us += 1e3 * a; ctx->last_shade_us += 1e3 * b;
+        float a = 0.f, b = 0.f, c = 0.f;
+        cudaEventElapsedTime(&c, ctx->wave_events[4 * i], ctx->wave_events[4 * i + 1]);
+        cudaEventElapsedTime(&a, ctx->wave_events[4 * i + 1], ctx->wave_events[4 * i + 2]);
+        cudaEventElapsedTime(&b, ctx->wave_events[4 * i + 2], ctx->wave_events[4 * i + 3]);
+        ctx->last_trace_us += 1e3 * a; ctx->last_shade_us += 1e3 * b; ctx->last_sort_us += 1e3 * c;
     }
     ctx->last_trace_launches = (uint64_t)ctx->wave_timed_rounds;
     ctx->wave_timed_rounds = 0;
@@ -219,7 +248,7 @@ int launch_wave(ptgpu_ctx* ctx, const Scene& sc, RenderJob job)
     const int tiles_x = (job.w + WF_TILE - 1) / WF_TILE, tiles_y = (job.h + WF_TILE - 1) / WF_TILE;
     // slots per pixel: the largest power of two <= the sample count that keeps the pool in budget
     const size_t n_pix_padded = (size_t)tiles_x * tiles_y * WF_TILE * WF_TILE;
-    const size_t bytes_per_slot = 16 * 9 + 4 + 8 + 4 + 5 * 4 + 1;
+    const size_t bytes_per_slot = 16 * 9 + 4 + 8 + 4 + 10 * 4 + 1;
     uint32_t lanes = 1, lane_shift = 0;
     while(lanes * 2 <= (uint32_t)job.s_count && lanes * 2 <= (uint32_t)ctx->max_lanes &&
           n_pix_padded * (lanes * 2) * bytes_per_slot <= ctx->pool_budget_bytes && n_pix_padded * (lanes * 2) < 0x7FFF0000ull)
@@ -231,7 +260,8 @@ int launch_wave(ptgpu_ctx* ctx, const Scene& sc, RenderJob job)
         o_sd = carve(16ull * n_slots), o_hit = carve(16ull * n_slots), o_prim = carve(4ull * n_slots),
         o_att = carve(16ull * n_slots), o_con = carve(16ull * n_slots), o_nee = carve(16ull * n_slots),
         o_sum = carve(16ull * n_slots), o_cur = carve(8ull * n_slots), o_vis = carve(4ull * n_slots),
-        o_qt = carve(4ull * 3ull * (n_slots + 64)), o_st = carve(n_slots), o_qf = carve(4ull * (n_slots + 64)), o_qn = carve(4ull * (n_slots + 64)), o_cnt = carve(sizeof(WaveCounters)), o_stats = carve(40 * 8);
+        o_qt = carve(4ull * 3ull * (n_slots + 64)), o_qk = carve(4ull * 3ull * (n_slots + 64)), o_qs = carve(4ull * 2ull * (n_slots + 64)),
+        o_sh = carve(4ull * 2ull * WF_SORT_BINS), o_st = carve(n_slots), o_qf = carve(4ull * (n_slots + 64)), o_qn = carve(4ull * (n_slots + 64)), o_cnt = carve(sizeof(WaveCounters)), o_stats = carve(40 * 8);
     if(ctx->wave_mem.reserve(off) != cudaSuccess) return -1;
     if(!ctx->wave_flag_host)
     {
@@ -245,6 +275,8 @@ int launch_wave(ptgpu_ctx* ctx, const Scene& sc, RenderJob job)
     wb.atten = (float4*)(m + o_att); wb.contrib = (float4*)(m + o_con); wb.nee = (float4*)(m + o_nee);
     wb.sum = (float4*)(m + o_sum); wb.cursor = (int2*)(m + o_cur); wb.visible = (uint32_t*)(m + o_vis);
     wb.q_trace = (uint32_t*)(m + o_qt); wb.status = m + o_st;
+    wb.q_key = (uint32_t*)(m + o_qk); wb.q_sorted = (uint32_t*)(m + o_qs); wb.sort_hist = (uint32_t*)(m + o_sh);
+    wb.sort = ctx->sort && ctx->bvh == 1 ? 1 : 0;
     wb.q_far = (uint32_t*)(m + o_qf); wb.q_near = (uint32_t*)(m + o_qn);
     wb.cnt = (WaveCounters*)(m + o_cnt);
     wb.stats = (unsigned long long*)(m + o_stats);
@@ -264,29 +296,37 @@ int launch_wave(ptgpu_ctx* ctx, const Scene& sc, RenderJob job)
     const int max_rounds = samples_per_slot * (sc.max_bounces + 1) + 2;
     const int check_every = 8;
     int rounds = 0;
-    // three events per round (trace begin, trace end, shade end) for the first WAVE_TIMED_ROUNDS rounds
+    // four events per round (round begin, trace begin, trace end, shade end) for the first WAVE_TIMED_ROUNDS rounds
     const int WAVE_TIMED_ROUNDS = 48;
     if(ctx->wave_events.empty())
     {
-        ctx->wave_events.resize(3 * WAVE_TIMED_ROUNDS);
+        ctx->wave_events.resize(4 * WAVE_TIMED_ROUNDS);
         for(auto& e : ctx->wave_events) if(cudaEventCreate(&e) != cudaSuccess) return -1;
     }
     for(;;)
     {
         for(int b = 0; b < check_every && rounds < max_rounds; ++b, ++rounds)
         {
-            wf_generate_kernel<<<sms * 4, 256, 0, st>>>(sc, job, wb);
             const bool timed = rounds < WAVE_TIMED_ROUNDS;
-            if(timed) cudaEventRecord(ctx->wave_events[3 * rounds], st);
-            if(ctx->bvh == 1) wf_trace_cw_kernel<<<sms * WF_CW_BLOCKS, WF_TRACE_THREADS, 0, st>>>(sc, job, wb);
-            else wf_trace_kernel<<<sms * 6, WF_TRACE_THREADS, 0, st>>>(sc, job, wb);
-            if(timed) cudaEventRecord(ctx->wave_events[3 * rounds + 1], st);
-            if(ctx->validate && ctx->bvh == 1) wf_validate_kernel<<<sms * 8, 128, 0, st>>>(sc, job, wb, wb.stats);
+            if(timed) cudaEventRecord(ctx->wave_events[4 * rounds], st);
+            if(wb.sort && rounds > 0)
+            {   // the bounce and shadow rays the previous round's shading appended (round 0 has primary rays only)
+                cudaMemsetAsync(wb.sort_hist, 0, 4ull * 2ull * WF_SORT_BINS, st);
+                wf_sort_count_kernel<<<dim3(sms * 2, 2), WF_SORT_THREADS, 0, st>>>(wb);
+                wf_sort_scan_kernel<<<2, 1024, 0, st>>>(wb);
+                wf_sort_scatter_kernel<<<dim3(sms * 2, 2), WF_SORT_THREADS, 0, st>>>(wb);
+                launches += 3;
+            }
+            wf_generate_kernel<<<sms * 4, 256, 0, st>>>(sc, job, wb);
+            if(timed) cudaEventRecord(ctx->wave_events[4 * rounds + 1], st);
+            wf_trace_cw_kernel<<<sms * WF_CW_BLOCKS, WF_TRACE_THREADS, 0, st>>>(sc, job, wb);
+            if(timed) cudaEventRecord(ctx->wave_events[4 * rounds + 2], st);
+            if(ctx->validate) wf_validate_kernel<<<sms * 8, 128, 0, st>>>(sc, job, wb, wb.stats);
             wf_phase_kernel<<<1, 32, 0, st>>>(wb, 1, nullptr);
             wf_classify_kernel<<<sms * 8, 256, 0, st>>>(wb);
             wf_shade_kernel<true><<<sms * WF_SHADE_GRID, 128, 0, st>>>(sc, job, wb);
             wf_shade_kernel<false><<<sms * WF_SHADE_GRID, 128, 0, st>>>(sc, job, wb);
-            if(timed) cudaEventRecord(ctx->wave_events[3 * rounds + 2], st);
+            if(timed) cudaEventRecord(ctx->wave_events[4 * rounds + 3], st);
             wf_phase_kernel<<<1, 32, 0, st>>>(wb, 2, ctx->wave_flag.p);
             launches += 7;
         }
@@ -560,11 +600,61 @@ static int upload_static_common(
     CK(cudaMemcpy(ctx->winst.p, w.instances.data(), n_static * sizeof(WideInstance), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(ctx->wtlas.p, w.tlas.data(), w.tlas.size() * sizeof(WideNode), cudaMemcpyHostToDevice));
     ctx->n_wtlas = w.tlas.size();
-    CK(ctx->cwnodes.reserve(w.cw_nodes.size()));
-    CK(ctx->cwtris.reserve(w.cw_tris.size()));
+    // flat static scene: appended to the compressed node / triangle arrays (its indices are absolute)
+    std::shared_ptr<const FlatScene> flat;
+    ctx->have_flat = false; ctx->flat_root = 0xFFFFFFFFu;
+    if(ctx->flat)
+    {
+        const uint32_t node_base = (uint32_t)(w.cw_nodes.size() / 5), tri_base = (uint32_t)(w.cw_tris.size() / 3);
+        uint64_t h = 0xCBF29CE484222325ull;
+        h = hash_bytes(h, instances, n_static * sizeof(ptgpu_tlas_instance));
+        h = hash_bytes(h, indices, n_indices * 4);
+        h = hash_bytes(h, pos, n_verts * sizeof(ptgpu_float3));
+        h = hash_bytes(h, &node_base, 4); h = hash_bytes(h, &tri_base, 4);
+        std::lock_guard<std::mutex> lock(g_flat_mutex);   // a second context waits for the first one's build
+        auto it = g_flat_cache.find(h);
+        if(it != g_flat_cache.end()) flat = it->second;
+        else
+        {
+            auto fs = std::make_shared<FlatScene>();
+            if(!build_flat_scene(w, indices, pos, instances, n_static, node_base, tri_base, *fs, err))
+                return fail(ctx, "flat scene build failed: %s", err.c_str());
+            if(2 * fs->depth + 8 > (uint32_t)CW_STACK)
+                return fail(ctx, "flat scene: BVH depth %u needs a deeper traversal stack than CW_STACK", fs->depth);
+            if(g_flat_cache.size() >= 2) g_flat_cache.erase(g_flat_cache.begin());
+            g_flat_cache[h] = fs;
+            flat = fs;
+        }
+        ctx->have_flat = true;
+        ctx->flat_root = node_base; ctx->flat_top = flat->n_top; ctx->flat_depth = flat->depth;
+        ctx->flat_tris = flat->n_tris; ctx->flat_nodes = flat->nodes.size() / 5;
+        ctx->flat_build_seconds = flat->build_seconds;
+    }
+    {   // ray-sort grid over the static scene
+        float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+        for(const WideInstance& wi : w.instances)
+        {
+            lo[0] = std::min(lo[0], wi.lo.x); lo[1] = std::min(lo[1], wi.lo.y); lo[2] = std::min(lo[2], wi.lo.z);
+            hi[0] = std::max(hi[0], wi.hi.x); hi[1] = std::max(hi[1], wi.hi.y); hi[2] = std::max(hi[2], wi.hi.z);
+        }
+        const float cells[3] = {32.0f, 8.0f, 32.0f};
+        for(int a = 0; a < 3; ++a)
+        {
+            ctx->key_lo[a] = lo[a];
+            ctx->key_scale[a] = hi[a] > lo[a] ? cells[a] / (hi[a] - lo[a]) : 0.0f;
+        }
+    }
+    const size_t n_flat_nodes4 = flat ? flat->nodes.size() : 0, n_flat_tris4 = flat ? flat->tris.size() : 0;
+    CK(ctx->cwnodes.reserve(w.cw_nodes.size() + n_flat_nodes4));
+    CK(ctx->cwtris.reserve(w.cw_tris.size() + n_flat_tris4));
     CK(ctx->cw_inst_index.reserve(w.cw_inst_index.size()));
     CK(cudaMemcpy(ctx->cwnodes.p, w.cw_nodes.data(), w.cw_nodes.size() * sizeof(float4), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(ctx->cwtris.p, w.cw_tris.data(), w.cw_tris.size() * sizeof(float4), cudaMemcpyHostToDevice));
+    if(flat)
+    {
+        CK(cudaMemcpy(ctx->cwnodes.p + w.cw_nodes.size(), flat->nodes.data(), n_flat_nodes4 * sizeof(float4), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(ctx->cwtris.p + w.cw_tris.size(), flat->tris.data(), n_flat_tris4 * sizeof(float4), cudaMemcpyHostToDevice));
+    }
     CK(cudaMemcpy(ctx->cw_inst_index.p, w.cw_inst_index.data(), w.cw_inst_index.size() * 4, cudaMemcpyHostToDevice));
     ctx->have_static = true;
     ctx->have_frame = false;
@@ -652,7 +742,8 @@ int ptgpu_set_frame(
             if(seen[k]) return fail(ctx, "ptgpu_set_frame: subframe %zu dynamic set is not prefix + one range", i);
         if(a == n_dyn) { a = b = p; }
         // kernel encoding: x = prefix length p (ids n_static .. n_static+p), y = a | (b-a) << 20
-        if(a >= (1u << 20) || (b - a) >= (1u << 12)) return fail(ctx, "ptgpu_set_frame: too many dynamic instances");
+        if(a >= (1u << 20) || p + (b - a) > (uint32_t)PTGPU_MAX_DYNAMIC_PER_SUBFRAME)
+            return fail(ctx, "ptgpu_set_frame: subframe %zu sees %u dynamic instances (limit %d)", i, p + (b - a), PTGPU_MAX_DYNAMIC_PER_SUBFRAME);
         final_ranges[i] = make_uint2(p, a | ((b - a) << 20));
     }
     if(upload_frame_common(ctx, subframes, n_subframes, dyn_instances, n_dyn, final_ranges)) return 1;
@@ -699,7 +790,8 @@ int ptgpu_set_frame_ranges(
     for(size_t i = 0; i < n_subframes; ++i)
     {
         uint32_t a = dyn_begin[i], b = dyn_end[i];
-        if(a >= (1u << 20) || (b - a) >= (1u << 12)) return fail(ctx, "ptgpu_set_frame_ranges: too many dynamic instances");
+        if(a >= (1u << 20) || prefix + (b - a) > (uint32_t)PTGPU_MAX_DYNAMIC_PER_SUBFRAME)
+            return fail(ctx, "ptgpu_set_frame_ranges: subframe %zu sees %u dynamic instances (limit %d)", i, prefix + (b - a), PTGPU_MAX_DYNAMIC_PER_SUBFRAME);
         ranges[i] = make_uint2(prefix, a | ((b - a) << 20));
     }
     ctx->frame_has_ref_tlas = false;
@@ -966,6 +1058,11 @@ int ptgpu_set_option(ptgpu_ctx* ctx, const char* key, int64_t value)
     if(!strcmp(key, "node_threshold")) { if(value < 1 || value > 32) return fail(ctx, "node_threshold must be 1..32"); ctx->node_threshold = (int)value; return 0; }
     if(!strcmp(key, "node_burst")) { if(value < 1 || value > 64) return fail(ctx, "node_burst must be 1..64"); ctx->node_burst = (int)value; return 0; }
     if(!strcmp(key, "validate")) { ctx->validate = value != 0; return 0; }
+    if(!strcmp(key, "flat")) { if(value != 0 && value != 1) return fail(ctx, "flat must be 0 or 1");
+        if(value == 1 && ctx->have_static && !ctx->have_flat) return fail(ctx, "flat = 1 must be set before the scene is uploaded (the flat BVH is built at upload)");
+        ctx->flat = (int)value; return 0; }
+    if(!strcmp(key, "sort")) { if(value != 0 && value != 1) return fail(ctx, "sort must be 0 or 1"); ctx->sort = (int)value; return 0; }
+    if(!strcmp(key, "top_smem")) { if(value != 0 && value != 1) return fail(ctx, "top_smem must be 0 or 1"); ctx->top_smem = (int)value; return 0; }
     if(!strcmp(key, "lanes")) { if(value < 1 || value > 4096 || (value & (value - 1))) return fail(ctx, "lanes must be a power of two in 1..4096"); ctx->max_lanes = (int)value; return 0; }
     if(!strcmp(key, "pool_budget_mb")) { if(value < 1) return fail(ctx, "pool_budget_mb must be positive"); ctx->pool_budget_bytes = (size_t)value << 20; return 0; }
     if(!strcmp(key, "min_active")) { if(value < -1 || value > 32) return fail(ctx, "min_active must be -1..32"); ctx->min_active = (int)value; return 0; }
@@ -1022,6 +1119,31 @@ int ptgpu_host_flatten_check(
     return 1;
 }
 
+int ptgpu_host_flat_check(
+    const ptgpu_bvh_node* nodes, size_t n_nodes, const ptgpu_bvh_link* links, size_t n_links,
+    const uint32_t* indices, size_t n_indices, const ptgpu_float3* pos, size_t n_verts,
+    const ptgpu_tlas_instance* instances, size_t n_static, uint64_t out[8], char* err, size_t err_len)
+{
+    std::string e;
+    WideScene ws;
+    FlatScene fs;
+    if(err && err_len) err[0] = 0;
+    if(!nodes || !links || !indices || !pos || !instances || !out || n_links != 8 * n_nodes) e = "bad arguments";
+    else if(build_wide_scene(nodes, n_nodes, links, indices, n_indices, pos, n_verts, instances, n_static, ws, e))
+    {
+        const uint32_t node_base = (uint32_t)(ws.cw_nodes.size() / 5), tri_base = (uint32_t)(ws.cw_tris.size() / 3);
+        if(build_flat_scene(ws, indices, pos, instances, n_static, node_base, tri_base, fs, e))
+        {
+            uint64_t bad = verify_flat_scene(fs, node_base, tri_base, e);
+            out[0] = fs.n_tris; out[1] = fs.nodes.size() / 5; out[2] = fs.n_top; out[3] = fs.depth; out[4] = bad;
+            out[5] = (uint64_t)(1e3 * fs.build_seconds); out[6] = 0; out[7] = 0;
+            if(bad == 0) return 0;
+        }
+    }
+    if(err && err_len) { strncpy(err, e.c_str(), err_len - 1); err[err_len - 1] = 0; }
+    return 1;
+}
+
 int ptgpu_host_build_check(
     const uint32_t* indices, size_t n_indices, const ptgpu_float3* pos, size_t n_verts,
     const ptgpu_mesh* meshes, size_t n_meshes,
@@ -1052,6 +1174,11 @@ int ptgpu_get_stat(ptgpu_ctx* ctx, const char* key, uint64_t* out)
     if(!strcmp(key, "trace_us")) { wave_timing(ctx); *out = (uint64_t)(ctx->last_trace_us + 0.5); return 0; }
     if(!strcmp(key, "shade_us")) { wave_timing(ctx); *out = (uint64_t)(ctx->last_shade_us + 0.5); return 0; }
     if(!strcmp(key, "trace_launches")) { wave_timing(ctx); *out = ctx->last_trace_launches; return 0; }
+    if(!strcmp(key, "sort_us")) { wave_timing(ctx); *out = (uint64_t)(ctx->last_sort_us + 0.5); return 0; }
+    if(!strcmp(key, "flat_tris")) { *out = ctx->have_flat ? ctx->flat_tris : 0; return 0; }
+    if(!strcmp(key, "flat_nodes")) { *out = ctx->have_flat ? ctx->flat_nodes : 0; return 0; }
+    if(!strcmp(key, "flat_depth")) { *out = ctx->have_flat ? ctx->flat_depth : 0; return 0; }
+    if(!strcmp(key, "flat_build_ms")) { *out = ctx->have_flat ? (uint64_t)(1e3 * ctx->flat_build_seconds) : 0; return 0; }
     return fail(ctx, "unknown stat '%s'", key);
 }
 

@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Render snapshot frames through the C ABI (no oracle): the command ncu profiles.
-usage: prof_frame.py [--frames 520 ...] [--reps 2] [--kernel 0|1] [--traversal 0|1] [--spp N]"""
+usage: prof_frame.py [--frames 520 ...] [--reps 2] [--kernel 0|1] [--traversal 0|1] [--spp N] [--opt flat=0 --opt sort=0 ...]"""
 import argparse
 import os
 import sys
@@ -17,12 +17,16 @@ def main():
     ap.add_argument("--kernel", type=int, default=2)
     ap.add_argument("--traversal", type=int, default=0)
     ap.add_argument("--spp", type=int, default=256)
+    ap.add_argument("--opt", action="append", default=[], help="ptgpu_set_option pair key=value (applied before the upload)")
     args = ap.parse_args()
     pkg = ge.load_package()
     sio = pkg.scene_io
     cfg = pkg.Config.testing()
     cfg.spp = args.spp
     r = pkg.Renderer(cfg, 0)
+    for kv in args.opt:
+        k, v = kv.split("=")
+        r.set_option(k, int(v))
     r.upload_static(**sio.load_static(sio.static_path()))
     r.set_option("kernel", args.kernel)
     r.set_option("traversal", args.traversal)
