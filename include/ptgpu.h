@@ -312,6 +312,34 @@ int ptgpu_set_animation_frame(ptgpu_ctx* ctx, const ptgpu_anim* anim, uint32_t f
  * About the uploaded scene: "flat_tris", "flat_nodes", "flat_depth", "flat_build_ms" (0 without a flat scene). */
 int ptgpu_get_stat(ptgpu_ctx* ctx, const char* key, uint64_t* out);
 
+/* ---- sub-function evaluator (parity tests) ----------------------------------------------------- */
+
+/* One device function of the path per item, on caller-supplied inputs: each can be compared directly with
+ * the reference function it restates instead of only through whole paths. Item i reads in[24*i ..] and
+ * writes out[32*i ..] (floats; uint32 values as the bits of a float). Functions that look at the scene
+ * need an uploaded scene and frame. */
+enum ptgpu_fn
+{
+    PTGPU_FN_RAND4 = 0,           /* generate_uniform_random4, math.hh:475-485. in: state[4] (bits) -> state[4] (bits), u[4] */
+    PTGPU_FN_FILM_OFFSET = 1,     /* sample_gaussian_weighted_disk(u, 0.4), path_tracer.hh:19-25. in: u[2] -> offset[2] */
+    PTGPU_FN_CAMERA_RAY = 2,      /* get_camera_ray, path_tracer.hh:429-450. in: u[2], coord[2], subframe -> dir[3], origin[3] */
+    PTGPU_FN_GGX_VNDF = 3,        /* sample_ggx_vndf, path_tracer.hh:67-83. in: view[3], roughness, u[2] -> h[3] */
+    PTGPU_FN_BSDF = 4,            /* bsdf, path_tracer.hh:184-222. in: light[3], view[3], albedo[3], roughness, metallic,
+                                   * transmission, eta -> attenuation[3], pdf */
+    PTGPU_FN_SAMPLE_BSDF = 5,     /* sample_bsdf, path_tracer.hh:224-296. in: u[3], view[3], albedo[3], roughness, metallic,
+                                   * transmission, eta -> dir[3], attenuation[3], pdf (negative: delta lobe) */
+    PTGPU_FN_SKY_ATTENUATION = 6, /* nishita_atmosphere_attenuation(jitter, 8, pos, view, 1e9), path_tracer.hh:456-497.
+                                   * in: jitter, pos[3], view[3] -> attenuation[3] */
+    PTGPU_FN_SKY_SCATTERING = 7,  /* nishita_atmosphere_scattering, path_tracer.hh:499-588. in: seed[4] (bits), light dir[3],
+                                   * light color[3], cos_solid_angle, pos[3], view[3], tmax -> attenuation[3], in_scatter[3], seed[4] */
+    PTGPU_FN_SAMPLE_CONE = 8,     /* sample_cone, path_tracer.hh:40-48. in: dir[3], cos_theta_min, u[2] -> dir[3] */
+    PTGPU_FN_SHADOW_RAY = 9,      /* trace_shadow_ray, path_tracer.hh:415-427. in: origin[3], dir[3], tmin, tmax, subframe -> occluded */
+    PTGPU_FN_TRACE_RAY = 10,      /* trace_ray, path_tracer.hh:340-412. in: origin[3], dir[3], tmin, subframe -> thit, pos[3],
+                                   * tbn columns[9], albedo[3], roughness, metallic, emission, transmission, eta, nee_pdf */
+    PTGPU_FN_COUNT = 11
+};
+int ptgpu_debug_eval(ptgpu_ctx* ctx, int32_t fn, const float* in, size_t n, float* out);
+
 /* ---- OBJ/MTL loader: load_mesh, mesh.cc:104-265, without the reference's mesh.cc ----- */
 
 /* A growing set of mesh buffers = `mesh_buffers` (mesh.hh:31-43): every ptgpu_meshes_load_obj appends one

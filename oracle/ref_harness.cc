@@ -295,6 +295,117 @@ int ref_restore_scene()
     return 0;
 }
 
+/* Sub-function evaluator for the direct parity tests: calls ONE reference
+ * function per item on caller-supplied inputs. Item i reads in[24*i ..] and writes out[32*i ..]; the
+ * function codes and layouts are the PTGPU_FN_* ones of include/ptgpu.h (the device twin is
+ * ptgpu_debug_eval). uint32 values travel as the bits of a float. */
+static inline uint32_t fbits(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+static inline float bitsf(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
+
+static pt_context make_ctx(const scene& s, uint32_t subframe_index)
+{
+    const subframe& sf = s.subframes[subframe_index];   /* path_tracer.hh:655-684 */
+    pt_context ctx;
+    ctx.tlas = sf.tlas;
+    ctx.instances = s.instances.data();
+    ctx.node_array = s.bvh_buf.nodes.data();
+    ctx.link_array = s.bvh_buf.links.data();
+    ctx.mesh_indices = s.mesh_buf.indices.data();
+    ctx.mesh_pos = s.mesh_buf.pos.data();
+    ctx.mesh_normal = s.mesh_buf.normal.data();
+    ctx.mesh_albedo = s.mesh_buf.albedo.data();
+    ctx.mesh_material = s.mesh_buf.material.data();
+    ctx.light = sf.light;
+    return ctx;
+}
+
+int ref_eval(int32_t fn, const float* in_all, int64_t n, float* out_all)
+{
+    for(int64_t i = 0; i < n; ++i)
+    {
+        const float* in = in_all + 24 * i;
+        float* out = out_all + 32 * i;
+        for(int k = 0; k < 32; ++k) out[k] = 0.0f;
+        switch(fn)
+        {
+        case 0: { /* generate_uniform_random4, math.hh:475-485 */
+            uint4 s = {fbits(in[0]), fbits(in[1]), fbits(in[2]), fbits(in[3])};
+            float4 f = generate_uniform_random4(&s);
+            out[0] = bitsf(s.x); out[1] = bitsf(s.y); out[2] = bitsf(s.z); out[3] = bitsf(s.w);
+            out[4] = f.x; out[5] = f.y; out[6] = f.z; out[7] = f.w;
+            break; }
+        case 1: { /* sample_gaussian_weighted_disk(u, 0.4), path_tracer.hh:19-25, :665 */
+            float2 o = sample_gaussian_weighted_disk(float2{in[0], in[1]}, 0.4f);
+            out[0] = o.x; out[1] = o.y;
+            break; }
+        case 2: { /* get_camera_ray, path_tracer.hh:429-450 */
+            if(!g_scene || (size_t)in[4] >= g_scene->subframes.size()) return 1;
+            float3 d, o;
+            get_camera_ray(g_scene->subframes[(size_t)in[4]].cam, float2{in[0], in[1]}, float2{in[2], in[3]}, &d, &o);
+            out[0] = d.x; out[1] = d.y; out[2] = d.z; out[3] = o.x; out[4] = o.y; out[5] = o.z;
+            break; }
+        case 3: { /* sample_ggx_vndf, path_tracer.hh:67-83 */
+            float3 h = sample_ggx_vndf(float3{in[0], in[1], in[2]}, in[3], float2{in[4], in[5]});
+            out[0] = h.x; out[1] = h.y; out[2] = h.z;
+            break; }
+        case 4: { /* bsdf, path_tracer.hh:184-222 */
+            float pdf = 0;
+            float3 a = bsdf(float3{in[0], in[1], in[2]}, float3{in[3], in[4], in[5]}, float3{in[6], in[7], in[8]},
+                            in[9], in[10], in[11], in[12], &pdf);
+            out[0] = a.x; out[1] = a.y; out[2] = a.z; out[3] = pdf;
+            break; }
+        case 5: { /* sample_bsdf, path_tracer.hh:224-296 */
+            float3 dir, att; float pdf = 0;
+            sample_bsdf(float3{in[0], in[1], in[2]}, float3{in[3], in[4], in[5]}, float3{in[6], in[7], in[8]},
+                        in[9], in[10], in[11], in[12], &dir, &att, &pdf);
+            out[0] = dir.x; out[1] = dir.y; out[2] = dir.z; out[3] = att.x; out[4] = att.y; out[5] = att.z; out[6] = pdf;
+            break; }
+        case 6: { /* nishita_atmosphere_attenuation as nee_branch calls it, path_tracer.hh:456-497, :615-617 */
+            float3 a = nishita_atmosphere_attenuation(in[0], ATMOSPHERE_PRIMARY_ITERATIONS, float3{in[1], in[2], in[3]},
+                                                      float3{in[4], in[5], in[6]}, MAX_RAY_DIST);
+            out[0] = a.x; out[1] = a.y; out[2] = a.z;
+            break; }
+        case 7: { /* nishita_atmosphere_scattering, path_tracer.hh:499-588 (only ctx.light is read) */
+            uint4 s = {fbits(in[0]), fbits(in[1]), fbits(in[2]), fbits(in[3])};
+            pt_context ctx;
+            memset(&ctx, 0, sizeof(ctx));
+            ctx.light.direction = float3{in[4], in[5], in[6]};
+            ctx.light.color = float3{in[7], in[8], in[9]};
+            ctx.light.cos_solid_angle = in[10];
+            float3 att, sc;
+            nishita_atmosphere_scattering(&s, ctx, float3{in[11], in[12], in[13]}, float3{in[14], in[15], in[16]}, in[17], &att, &sc);
+            out[0] = att.x; out[1] = att.y; out[2] = att.z; out[3] = sc.x; out[4] = sc.y; out[5] = sc.z;
+            out[6] = bitsf(s.x); out[7] = bitsf(s.y); out[8] = bitsf(s.z); out[9] = bitsf(s.w);
+            break; }
+        case 8: { /* sample_cone, path_tracer.hh:40-48 */
+            float3 d = sample_cone(float3{in[0], in[1], in[2]}, in[3], float2{in[4], in[5]});
+            out[0] = d.x; out[1] = d.y; out[2] = d.z;
+            break; }
+        case 9: { /* trace_shadow_ray, path_tracer.hh:415-427 */
+            if(!g_scene || (size_t)in[8] >= g_scene->subframes.size()) return 1;
+            pt_context ctx = make_ctx(*g_scene, (uint32_t)in[8]);
+            out[0] = trace_shadow_ray(ctx, float3{in[0], in[1], in[2]}, float3{in[3], in[4], in[5]}, in[6], in[7]) ? 1.0f : 0.0f;
+            break; }
+        case 10: { /* trace_ray -> hit_info, path_tracer.hh:340-412 */
+            if(!g_scene || (size_t)in[7] >= g_scene->subframes.size()) return 1;
+            pt_context ctx = make_ctx(*g_scene, (uint32_t)in[7]);
+            hit_info hi = trace_ray(ctx, float3{in[0], in[1], in[2]}, float3{in[3], in[4], in[5]}, in[6]);
+            out[0] = hi.thit;
+            out[13] = hi.albedo.x; out[14] = hi.albedo.y; out[15] = hi.albedo.z;
+            out[18] = hi.emission; out[21] = hi.nee_pdf;
+            if(hi.thit >= 0)
+            {   /* a miss leaves the rest uninitialised (and unread, path_tracer.hh:697) */
+                out[1] = hi.pos.x; out[2] = hi.pos.y; out[3] = hi.pos.z;
+                for(int c = 0; c < 3; ++c) { out[4 + 3 * c] = hi.tbn.r[c].x; out[5 + 3 * c] = hi.tbn.r[c].y; out[6 + 3 * c] = hi.tbn.r[c].z; }
+                out[16] = hi.roughness; out[17] = hi.metallic; out[19] = hi.transmission; out[20] = hi.eta;
+            }
+            break; }
+        default: return 2;
+        }
+    }
+    return 0;
+}
+
 void ref_write_bmp(const char* name, uint32_t w, uint32_t h, const uint8_t* bgra)
 {
     write_bmp(name, w, h, 4, w * 4, bgra); /* main.cc:97-101 */

@@ -105,6 +105,8 @@ class Oracle:
         L.ref_setup_stress_scene.restype = C.c_int
         L.ref_restore_scene.restype = C.c_int
         L.ref_write_bmp.argtypes = [C.c_char_p, C.c_uint32, C.c_uint32, C.c_void_p]
+        L.ref_eval.argtypes = [C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]
+        L.ref_eval.restype = C.c_int
         self.config = RefConfig()
         L.ref_get_config(C.byref(self.config))
         self.loaded = False
@@ -212,6 +214,18 @@ class Oracle:
         self.lib.ref_trace_closest(of, df, tmin, tmax, subframe, rf, ru)
         return {"thit": rf[0], "bary": (rf[1], rf[2], rf[3]), "instance": ru[0],
                 "primitive": ru[1], "back_face": bool(ru[2])}
+
+    def eval(self, fn, inputs):
+        """One reference sub-function per row of `inputs` (n x <=24 floats; uint32 values as float bits):
+        the PTGPU_FN_* codes and layouts of include/ptgpu.h. Returns n x 32 floats."""
+        a = np.zeros((len(inputs), 24), np.float32)
+        src = np.asarray(inputs, np.float32)
+        a[:, :src.shape[1]] = src
+        out = np.zeros((len(inputs), 32), np.float32)
+        rc = self.lib.ref_eval(int(fn), a.ctypes.data, len(a), out.ctypes.data)
+        if rc != 0:
+            raise RuntimeError("ref_eval(%d) failed: %d" % (fn, rc))
+        return out
 
     def write_bmp(self, path, bgra):
         h, w = bgra.shape[:2]

@@ -95,13 +95,32 @@ PT_D void cw_set_space(CwState& st, v3 o, v3 d)
 // form costs one more instruction per byte (profiles/r01_trace_kernel_history.md).
 PT_D float u8f(uint32_t w, int j) { return (float)((w >> (8 * j)) & 0xFFu); }
 
+// Top levels of the flat BVH staged in shared memory (north_star: "staging the top levels in shared memory
+// and leaving the rest to L2"): nodes [base, base + n) of the node array are also at sm[5 * (index - base)].
+struct TopLevels
+{
+    const float4* sm;
+    uint32_t base, n;
+};
+constexpr uint32_t CW_TOP_NODES = 96;   // 7.5 KB per block
+
 // Box test of the eight children of one node; fills the node group (inner children hit) and the
 // leaf group (leaf payloads whose box was hit).
+template<bool TOP>
 PT_D void cw_intersect_node(const float4* __restrict__ nodes, uint32_t node_index, const CwState& st,
-                            uint2& ngroup, uint2& tgroup)
+                            uint2& ngroup, uint2& tgroup, const TopLevels& top)
 {
-    const float4* n = nodes + 5 * (size_t)node_index;
-    const float4 n0 = __ldg(n), n1 = __ldg(n + 1), n2 = __ldg(n + 2), n3 = __ldg(n + 3), n4 = __ldg(n + 4);
+    float4 n0, n1, n2, n3, n4;
+    if(TOP && node_index - top.base < top.n)
+    {
+        const float4* n = top.sm + 5 * (node_index - top.base);
+        n0 = n[0]; n1 = n[1]; n2 = n[2]; n3 = n[3]; n4 = n[4];
+    }
+    else
+    {
+        const float4* n = nodes + 5 * (size_t)node_index;
+        n0 = __ldg(n); n1 = __ldg(n + 1); n2 = __ldg(n + 2); n3 = __ldg(n + 3); n4 = __ldg(n + 4);
+    }
     const uint32_t ew = __float_as_uint(n0.w);
     const float sx = __uint_as_float((uint32_t)(((int)(ew << 24) >> 24) + 127) << 23);
     const float sy = __uint_as_float((uint32_t)(((int)(ew << 16) >> 24) + 127) << 23);
@@ -149,6 +168,14 @@ PT_D void cw_intersect_node(const float4* __restrict__ nodes, uint32_t node_inde
 // hit.inst of a world-space query phase: the instance comes from the triangle record
 #define CW_FLAT_INST 0xFFFFFFFEu
 
+// The world-space ray enters the flat static scene: its leaves are triangles (in_blas), stored in world space
+PT_D void cw_enter_flat(CwState& st)
+{
+    tri_preprocess(st.rd, st.axis, st.S);
+    st.in_blas = true;
+    st.cur_inst = CW_FLAT_INST;
+}
+
 // Query start: the subframe's dynamic instances (world-box test) go on the stack as one instance
 // group. Flat static scene: the query then starts IN the static world (its triangles are stored in world
 // space: no transform, no entry step), the dynamic group waits under an exit marker. Otherwise the static
@@ -179,6 +206,15 @@ PT_D void cw_begin(const Scene& sc, CwState& st, Stack& stack, uint32_t subframe
         st.ngroup = make_uint2(sc.cw_tlas_root, 0x80000000u);
         return;
     }
+    if(mask && sc.dyn_first)
+    {   // the per-frame instances first (the hero objects stand in front of the camera: their hits shorten the
+        // ray before the static world is walked); the static world waits on the stack as a node group
+        st.sp = 0;
+        stack.set(st.sp++, make_uint2(sc.flat_root, 0x80000000u));
+        st.tgroup = make_uint2(0x80000000u, mask);
+        st.ngroup = make_uint2(0u, 0u);
+        return;
+    }
     if(mask)
     {
         if(PARKED)
@@ -188,9 +224,7 @@ PT_D void cw_begin(const Scene& sc, CwState& st, Stack& stack, uint32_t subframe
         }
         stack.set(st.sp++, make_uint2(CW_MARK_X, 0u));
     }
-    tri_preprocess(rd, st.axis, st.S);
-    st.in_blas = true;
-    st.cur_inst = CW_FLAT_INST;
+    cw_enter_flat(st);
     st.ngroup = make_uint2(sc.flat_root, 0x80000000u);
 }
 
@@ -255,8 +289,8 @@ PT_D void cw_test_triangle(const Scene& sc, CwState& st, uint32_t tri)
 }
 
 // node phase: take the next child of the node group (highest bit = nearest in octant order), test it
-template<class Stack>
-PT_D void cw_node_phase(const Scene& sc, CwState& st, Stack& stack)
+template<bool TOP = false, class Stack>
+PT_D void cw_node_phase(const Scene& sc, CwState& st, Stack& stack, const TopLevels& top = TopLevels{nullptr, 0u, 0u})
 {
     if(st.ngroup.y > 0x00FFFFFFu)
     {
@@ -267,7 +301,7 @@ PT_D void cw_node_phase(const Scene& sc, CwState& st, Stack& stack)
         if(st.ngroup.y > 0x00FFFFFFu) stack.set(st.sp++, st.ngroup);
         const uint32_t slot = (child_bit - 24u) ^ (st.oct_inv4 & 0xFFu);
         const uint32_t rel = (uint32_t)__popc(hits_imask & ~(0xFFFFFFFFu << slot));
-        cw_intersect_node(sc.cwnodes, base + rel, st, st.ngroup, st.tgroup);
+        cw_intersect_node<TOP>(sc.cwnodes, base + rel, st, st.ngroup, st.tgroup, top);
     }
     else
     {   // the entry popped last was a leaf group
@@ -289,7 +323,7 @@ PT_D void cw_instance_phase(const Scene& sc, CwState& st, Stack& stack)
 
 // pop phase; returns false when the query is complete
 template<class Stack>
-PT_D bool cw_pop_phase(CwState& st, Stack& stack)
+PT_D bool cw_pop_phase(const Scene& sc, CwState& st, Stack& stack)
 {
     if(st.ngroup.y <= 0x00FFFFFFu)
     {
@@ -301,7 +335,12 @@ PT_D bool cw_pop_phase(CwState& st, Stack& stack)
             cw_set_space(st, st.ro, st.rd);
             st.ngroup = make_uint2(0u, 0u);
         }
-        else st.ngroup = e;
+        else
+        {
+            st.ngroup = e;
+            // a node group met in world space with a flat static scene is that scene's root (dyn_first)
+            if(!st.in_blas && e.y > 0x00FFFFFFu && sc.flat_root != 0xFFFFFFFFu) cw_enter_flat(st);
+        }
     }
     return true;
 }
@@ -326,7 +365,7 @@ PT_D bool trace_cw(const Scene& sc, uint32_t subframe, v3 origin, v3 dir, float 
             }
         }
         else if(st.tgroup.y) cw_instance_phase(sc, st, stack);
-        if(!cw_pop_phase(st, stack)) break;
+        if(!cw_pop_phase(sc, st, stack)) break;
     }
     hit = st.hit;
     return ANY ? hit.t >= 0.0f : hit.t >= 0.0f;

@@ -319,9 +319,19 @@ constexpr int CW_PEND = CW_PEND_N;
 #ifndef WF_CW_BLOCKS
 #define WF_CW_BLOCKS 7
 #endif
+template<bool TOP>
 __global__ void __launch_bounds__(WF_TRACE_THREADS, WF_CW_BLOCKS)
 wf_trace_cw_kernel(Scene sc, RenderJob job, WaveBuffers wb)
 {
+    // TOP: the first CW_TOP_NODES nodes of the flat BVH (its top levels, breadth-first) in shared memory
+    __shared__ float4 s_top[TOP ? 5 * CW_TOP_NODES : 1];
+    TopLevels top{s_top, sc.flat_root, 0u};
+    if(TOP && sc.flat_root != 0xFFFFFFFFu)
+    {
+        top.n = min(sc.flat_top, CW_TOP_NODES);
+        for(uint32_t i = threadIdx.x; i < 5u * top.n; i += WF_TRACE_THREADS) s_top[i] = __ldg(sc.cwnodes + 5 * (size_t)sc.flat_root + i);
+        __syncthreads();
+    }
     const unsigned lane = threadIdx.x & 31u;
     const uint32_t n_s0 = wb.cnt->n_seg[0], n_s1 = wb.cnt->n_seg[1], n_s2 = wb.cnt->n_seg[2];
     const uint32_t n_entries = n_s0 + n_s1 + n_s2;
@@ -432,7 +442,13 @@ wf_trace_cw_kernel(Scene sc, RenderJob job, WaveBuffers wb)
                     else
                     {
                         st.sp--;
-                        if(e.y > 0x00FFFFFFu) st.ngroup = e; else st.tgroup = e;
+                        if(e.y > 0x00FFFFFFu)
+                        {
+                            st.ngroup = e;
+                            // a node group met in world space with a flat static scene is that scene's root (dyn_first)
+                            if(!st.in_blas && sc.flat_root != 0xFFFFFFFFu) cw_enter_flat(st);
+                        }
+                        else st.tgroup = e;
                     }
                 }
             }
@@ -444,7 +460,7 @@ wf_trace_cw_kernel(Scene sc, RenderJob job, WaveBuffers wb)
 #ifdef WF_STATS
             const bool at_root = st.in_blas && st.ngroup.y == 0x80000000u;
 #endif
-            cw_node_phase(sc, st, stack);
+            cw_node_phase<TOP>(sc, st, stack, top);
 #ifdef WF_STATS
             if(at_root) { atomicAdd(&wb.stats[7], 1ull); if(st.ngroup.y <= 0x00FFFFFFu && st.tgroup.y == 0u) atomicAdd(&wb.stats[16], 1ull); }
 #endif

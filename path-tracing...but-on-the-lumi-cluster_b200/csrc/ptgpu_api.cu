@@ -5,6 +5,7 @@
 #include "pt_mega.cuh"
 #include "pt_wave.cuh"
 #include "pt_cwbvh.cuh"
+#include "pt_debug.cuh"
 #include "bvh_wide.hh"
 
 #include <algorithm>
@@ -87,6 +88,7 @@ struct ptgpu_ctx
     int flat = 1;                              // static instances as one world-space BVH (built at upload)
     int sort = 1;                              // wavefront: bounce and shadow rays sorted by octant + origin cell
     int top_smem = 0;                          // wavefront: top levels of the flat BVH staged in shared memory
+    int dyn_first = 0;                         // flat scene: per-frame instances are entered before the static world
 
     // static scene, reference layout
     DevBuf<float2> ref_nodes;     // 3 per node; static region then per-frame TLAS region
@@ -200,6 +202,7 @@ Scene make_scene(ptgpu_ctx* ctx)
     s.cw_tlas_root = ctx->wide_host.cw_tlas_root;
     s.flat_root = ctx->flat && ctx->have_flat ? ctx->flat_root : 0xFFFFFFFFu;
     s.flat_top = ctx->flat_top;
+    s.dyn_first = (uint32_t)ctx->dyn_first;
     for(int a = 0; a < 3; ++a) { s.key_lo[a] = ctx->key_lo[a]; s.key_scale[a] = ctx->key_scale[a]; }
     s.n_static = (uint32_t)ctx->n_static;
     s.n_subframes = (uint32_t)ctx->n_subframes;
@@ -319,7 +322,8 @@ int launch_wave(ptgpu_ctx* ctx, const Scene& sc, RenderJob job)
             }
             wf_generate_kernel<<<sms * 4, 256, 0, st>>>(sc, job, wb);
             if(timed) cudaEventRecord(ctx->wave_events[4 * rounds + 1], st);
-            wf_trace_cw_kernel<<<sms * WF_CW_BLOCKS, WF_TRACE_THREADS, 0, st>>>(sc, job, wb);
+            if(ctx->top_smem) wf_trace_cw_kernel<true><<<sms * WF_CW_BLOCKS, WF_TRACE_THREADS, 0, st>>>(sc, job, wb);
+            else wf_trace_cw_kernel<false><<<sms * WF_CW_BLOCKS, WF_TRACE_THREADS, 0, st>>>(sc, job, wb);
             if(timed) cudaEventRecord(ctx->wave_events[4 * rounds + 2], st);
             if(ctx->validate) wf_validate_kernel<<<sms * 8, 128, 0, st>>>(sc, job, wb, wb.stats);
             wf_phase_kernel<<<1, 32, 0, st>>>(wb, 1, nullptr);
@@ -1044,6 +1048,29 @@ int ptgpu_pcg4d(ptgpu_ctx* ctx, uint32_t* states, size_t n, int32_t steps)
     return 0;
 }
 
+int ptgpu_debug_eval(ptgpu_ctx* ctx, int32_t fn, const float* in, size_t n, float* out)
+{
+    if(!ctx) return 1;
+    if(fn < 0 || fn >= PTGPU_FN_COUNT) return fail(ctx, "ptgpu_debug_eval: unknown function %d", fn);
+    if(n == 0) return 0;
+    if(!in || !out) return fail(ctx, "ptgpu_debug_eval: null argument");
+    const bool needs_scene = fn == PTGPU_FN_CAMERA_RAY || fn == PTGPU_FN_SHADOW_RAY || fn == PTGPU_FN_TRACE_RAY;
+    if(needs_scene && check_ready(ctx)) return 1;
+    if(use(ctx)) return 1;
+    CK(ctx->scratch_a.reserve(n * 24 * 4)); CK(ctx->scratch_b.reserve(n * 32 * 4));
+    CK(cudaMemcpyAsync(ctx->scratch_a.p, in, n * 24 * 4, cudaMemcpyHostToDevice, ctx->stream));
+    Scene sc = make_scene(ctx);
+    const int threads = 64; const int blocks = (int)((n + threads - 1) / threads);
+    if(ctx->traversal == 1)
+        debug_eval_kernel<LinksTrav<false>><<<blocks, threads, 0, ctx->stream>>>(sc, fn, (const float*)ctx->scratch_a.p, n, (float*)ctx->scratch_b.p);
+    else
+        debug_eval_kernel<CwTrav><<<blocks, threads, 0, ctx->stream>>>(sc, fn, (const float*)ctx->scratch_a.p, n, (float*)ctx->scratch_b.p);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, ctx->scratch_b.p, n * 32 * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
 int ptgpu_set_option(ptgpu_ctx* ctx, const char* key, int64_t value)
 {
     if(!ctx || !key) return 1;
@@ -1062,6 +1089,7 @@ int ptgpu_set_option(ptgpu_ctx* ctx, const char* key, int64_t value)
         if(value == 1 && ctx->have_static && !ctx->have_flat) return fail(ctx, "flat = 1 must be set before the scene is uploaded (the flat BVH is built at upload)");
         ctx->flat = (int)value; return 0; }
     if(!strcmp(key, "sort")) { if(value != 0 && value != 1) return fail(ctx, "sort must be 0 or 1"); ctx->sort = (int)value; return 0; }
+    if(!strcmp(key, "dyn_first")) { if(value != 0 && value != 1) return fail(ctx, "dyn_first must be 0 or 1"); ctx->dyn_first = (int)value; return 0; }
     if(!strcmp(key, "top_smem")) { if(value != 0 && value != 1) return fail(ctx, "top_smem must be 0 or 1"); ctx->top_smem = (int)value; return 0; }
     if(!strcmp(key, "lanes")) { if(value < 1 || value > 4096 || (value & (value - 1))) return fail(ctx, "lanes must be a power of two in 1..4096"); ctx->max_lanes = (int)value; return 0; }
     if(!strcmp(key, "pool_budget_mb")) { if(value < 1) return fail(ctx, "pool_budget_mb must be positive"); ctx->pool_budget_bytes = (size_t)value << 20; return 0; }

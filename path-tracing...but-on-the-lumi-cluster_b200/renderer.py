@@ -165,6 +165,16 @@ class Renderer:
         self._check(self.lib.ptgpu_pcg4d(self.ctx, _ptr(s), s.shape[0], steps), "ptgpu_pcg4d")
         return s
 
+    def debug_eval(self, fn, inputs):
+        """ptgpu_debug_eval: one device function of the path per row of `inputs` (n x <= 24 floats, uint32
+        values as float bits; PTGPU_FN_* of include/ptgpu.h). Returns n x 32 floats."""
+        src = np.asarray(inputs, np.float32)
+        a = np.zeros((src.shape[0], 24), np.float32)
+        a[:, :src.shape[1]] = src
+        out = np.zeros((src.shape[0], 32), np.float32)
+        self._check(self.lib.ptgpu_debug_eval(self.ctx, int(fn), _ptr(a), a.shape[0], _ptr(out)), "ptgpu_debug_eval")
+        return out
+
     # -- device-resident rendering ---------------------------------------------------------
     def render_async(self):
         self._check(self.lib.ptgpu_render_async(self.ctx), "ptgpu_render_async")
