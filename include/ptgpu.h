@@ -241,7 +241,10 @@ int ptgpu_last_render_ms(ptgpu_ctx* ctx, float* ms, int32_t* launches);
  *              Set it before the scene is uploaded. Per-frame instances are instances either way.
  * "sort":      1 (default) = the wavefront renderer sorts bounce and shadow rays by direction octant and
  *              origin cell before every traversal launch; 0 = queue order.
- * "top_smem":  1 = the traversal kernel stages the top levels of the flat BVH in shared memory (default 0).
+ * "dyn_first": 1 (default) = with the flat scene a query enters the per-frame instances (the hero objects in
+ *              front of the camera) before the static world; 0 = after.
+ * "top_smem":  1 = the traversal kernel stages the top levels of the flat BVH in shared memory (default 0:
+ *              measured 0-3 % slower, profiles/r02_trace_kernel_history.md).
  * "lanes", "pool_budget_mb": path slots per pixel of the wavefront pool (power of two) and its budget
  * "min_active", "node_threshold", "node_burst", "tri_threshold", "xform_threshold": warp scheduling
  *              of the traversal kernels (see csrc/pt_wave.cuh); results do not depend on them

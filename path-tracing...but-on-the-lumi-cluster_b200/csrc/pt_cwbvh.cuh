@@ -354,7 +354,8 @@ PT_D bool trace_cw(const Scene& sc, uint32_t subframe, v3 origin, v3 dir, float 
     cw_begin<false>(sc, st, stack, subframe, origin, dir, tmin, tmax, ANY);
     for(;;)
     {
-        cw_node_phase(sc, st, stack);
+        // (a leaf group may already wait in tgroup: the per-frame instances of a dyn_first query start there)
+        if(st.ngroup.y > 0x00FFFFFFu || st.tgroup.y == 0u) cw_node_phase(sc, st, stack);
         if(st.in_blas)
         {
             while(st.tgroup.y)

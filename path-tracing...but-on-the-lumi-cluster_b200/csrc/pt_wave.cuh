@@ -316,8 +316,11 @@ constexpr int WF_FETCH_CHUNK = WF_FETCH_CHUNK_N;
 #endif
 constexpr int CW_PEND = CW_PEND_N;
 
+// Resident blocks per SM. With the instanced scene 7 (72 registers, no spills) beat 8 (64 registers, 110 B of
+// spills) by 7 %; with the flat scene the kernel waits on memory more (L1 hit 47-65 %, long_scoreboard the top
+// stall in the bounce rounds) and 8 blocks = 32 warps win 3.5 % (32 B spill stores, 76 B loads).
 #ifndef WF_CW_BLOCKS
-#define WF_CW_BLOCKS 7
+#define WF_CW_BLOCKS 8
 #endif
 template<bool TOP>
 __global__ void __launch_bounds__(WF_TRACE_THREADS, WF_CW_BLOCKS)

@@ -88,7 +88,7 @@ struct ptgpu_ctx
     int flat = 1;                              // static instances as one world-space BVH (built at upload)
     int sort = 1;                              // wavefront: bounce and shadow rays sorted by octant + origin cell
     int top_smem = 0;                          // wavefront: top levels of the flat BVH staged in shared memory
-    int dyn_first = 0;                         // flat scene: per-frame instances are entered before the static world
+    int dyn_first = 1;                         // flat scene: per-frame instances are entered before the static world
 
     // static scene, reference layout
     DevBuf<float2> ref_nodes;     // 3 per node; static region then per-frame TLAS region

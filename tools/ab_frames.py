@@ -20,6 +20,11 @@ sys.path.insert(0, ROOT)
 import __graft_entry__ as ge  # noqa: E402
 
 
+# options a config does not name go back to these (options are sticky in a context)
+DEFAULTS = {"sort": 1, "dyn_first": 1, "top_smem": 0, "node_threshold": 16, "node_burst": 2, "tri_threshold": 8,
+            "xform_threshold": 4, "min_active": -1}
+
+
 def parse_configs(text):
     out = []
     for part in text.split(";"):
@@ -95,7 +100,7 @@ def main():
                       trel.max() if trel.size else 0.0, (ua[same, 2] == ub[same, 2]).mean()), flush=True)
         for c in configs:
             r = ctx[c.get("flat", 1)]
-            for k, v in c.items():
+            for k, v in {**DEFAULTS, **c}.items():
                 if k != "flat":
                     r.set_option(k, v)
             name = ",".join("%s=%d" % kv for kv in c.items())
