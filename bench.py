@@ -7,10 +7,14 @@
 A step renders ONE animation frame at the shipped config.hh size (640x360, 256 spp, 4 bounces =
 58,982,400 paths). The frames are scene snapshots of the reference's own animation (the arrays its
 setup_animation_frame() hands to baseline_render, dumped by oracle/make_snapshots.py where the
-reference is mounted; stand-in terrain/pine/bunny geometry). Step i of rank r uses
-snapshot (i*N + r) mod 14, frames spread over the 1800-frame animation, so K steps sample the
-"full default animation" workload of BASELINE.json configs[2]; `--steps 1800` walks it 128 times.
-Frames are sharded over ranks with no data-path collective (weak scaling: K frames per rank).
+reference is mounted; stand-in terrain/pine/bunny geometry). The K steps of a run walk
+the 14 snapshot frames in order (step j -> snapshot j mod 14, frames spread over the 1800-frame animation:
+the "full default animation" workload of BASELINE.json configs[2]); rank r renders the same K-frame list
+rotated by r (step i -> list[(i + r) mod K]), so at every N every rank renders exactly the same multiset
+of frames and v_N / (N v_1) measures scaling, not the frame mix (frame 0 is 3.5x cheaper than the mean).
+Frames are sharded over ranks with no data-path collective (weak scaling: K frames per rank). After the
+timed loops every 10th frame of the real animation (180 frames, sharded over the ranks) is rendered through
+the frame-setup module and read back: `animation_seconds_measured` = that wall time x 10.
 
 Printed JSON (rank 0, one line): metric Mpaths/s; `value` = device-resident throughput (static scene
 in HBM, per-frame input = ~40 KB of transforms), `e2e` = the same through ptgpu_render_frame() with
@@ -203,9 +207,10 @@ def workload_config(n_gpus, animation=False):
     return {"workload": "full default animation, config.hh TESTING size: 640x360, 256 spp, 4 bounces, 32 motion-blur subframes; "
                         "one step = one frame (58,982,400 paths); " + (
                             "steps walk the 1800-frame animation at a uniform stride" if animation else
-                            "steps cycle 14 frames spread over the 1800-frame animation (0,100,200,330,420,520,660,800,1000,1100,1250,1400,1600,1750)"),
+                            "steps walk 14 frames spread over the 1800-frame animation (0,100,200,330,420,520,660,800,1000,1100,1250,1400,1600,1750); "
+                            "every rank renders the same K-frame list, rotated by its rank"),
             "frames_per_step": 1, "paths_per_step": PATHS_PER_FRAME, "parallelism": "frames sharded over %d GPU(s), no collective" % n_gpus,
-            "l2_policy": "every step renders a different frame and streams the 10.9 GB path-state pool (one slot per path) through HBM, far larger than the 126 MB L2"}
+            "l2_policy": "every step renders a different frame and streams the 11.9 GB path-state pool (one slot per path) and the 1 GB flat scene through HBM, far larger than the 126 MB L2"}
 
 
 def main():
@@ -216,6 +221,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--kernel", type=int, default=None, help="0 megakernel, 1 tiles, 2 wavefront (default)")
+    ap.add_argument("--animation-stride", type=int, default=10,
+                    help="after the timed loops render every S-th frame of the 1800-frame animation end to end (0 = skip)")
     ap.add_argument("--animation", action="store_true",
                     help="walk the animation itself: step i renders frame (i*N + rank) * 1800 / (steps*N) through the "
                          "frame-setup module (--steps 1800 --gpus 1 = every frame); no roofline (flops are frozen for the 14 snapshot frames)")
@@ -271,7 +278,8 @@ def main():
     def frame_of(step):
         if args.animation:
             return ((step * world + rank) * ANIMATION_FRAMES) // (args.steps * world)
-        return frames[(step * world + rank) % len(frames)]
+        # the same K-frame list on every rank, rotated by the rank: identical multisets at every N
+        return pkg.sharding.bench_frame(step, rank, max(args.steps, 1), frames)
 
     def set_frame(f):
         if anim is not None:
@@ -350,6 +358,31 @@ def main():
     sampler.stop_flag.set()
     sampler.join(timeout=2)
 
+    # ---- loop C: the animation itself, every S-th frame, end to end (keyframe replay on the host, ~30 KB up,
+    #      render, BGRA frame back to pinned host memory), frames dealt round-robin to the ranks. This is the
+    #      loop of main.cc:78-102 without the file write; S = 1 and one rank is the whole 1800-frame animation.
+    anim_wall, anim_frames = 0.0, 0
+    if anim is not None and args.animation_stride > 0 and not args.animation:
+        todo = list(range(0, ANIMATION_FRAMES, args.animation_stride))
+        mine = todo[rank::world]
+        barrier()
+        t0 = time.perf_counter()
+        for f in mine:
+            sub, dyn, db, de = anim.frame(f)
+            r.set_frame_ranges(sub, dyn, db, de)
+            r.render(out=out_np)
+        barrier()
+        anim_wall, anim_frames = time.perf_counter() - t0, len(todo)
+
+    clocks_mine = sampler.result()
+    mine_stats = torch.tensor([wall_a, wall_b, dev_ms / 1e3, trace_us / 1e6, float(clocks_mine["sm_mhz"] or 0.0), anim_wall],
+                              dtype=torch.float64, device="cuda")
+    per_rank = [mine_stats.clone() for _ in range(world)]
+    if dist is not None:
+        dist.all_gather(per_rank, mine_stats)
+    per_rank = [[float(x) for x in t.tolist()] for t in per_rank]
+    anim_wall = max(p[5] for p in per_rank)
+
     times = torch.tensor([wall_a, wall_b, dev_ms / 1e3], dtype=torch.float64, device="cuda")
     sums = torch.tensor([float(launches), flops], dtype=torch.float64, device="cuda")
     if dist is not None:
@@ -379,6 +412,16 @@ def main():
             "data": "synthetic (reference animation via scene snapshots; stand-in terrain/pine/bunny assets)",
             "config": workload_config(world, args.animation),
             "animation_seconds_estimate": round(ANIMATION_FRAMES * (wall_a / args.steps) / world, 1),
+            # measured: every S-th frame of the animation rendered end to end on these N GPUs, wall x S
+            "animation_seconds_measured": round(anim_wall * args.animation_stride, 1) if anim_frames else None,
+            "animation_sample": ("frames 0,%d,..,%d (%d frames) in %.2f s on %d GPU(s), ptgpu_anim_frame + ptgpu_set_frame_ranges + ptgpu_render"
+                                 % (args.animation_stride, ANIMATION_FRAMES - args.animation_stride, anim_frames, anim_wall, world)) if anim_frames else None,
+            # every rank's own clock: which GPU is the slow one, and by how much (value uses the max)
+            "per_rank": {"wall_ms_per_step": [round(1e3 * p[0] / args.steps, 3) for p in per_rank],
+                         "e2e_ms_per_step": [round(1e3 * p[1] / args.steps, 3) for p in per_rank],
+                         "device_ms_per_step": [round(1e3 * p[2] / args.steps, 3) for p in per_rank],
+                         "trace_ms_per_step": [round(1e3 * p[3] / args.steps, 3) for p in per_rank],
+                         "sm_mhz": [p[4] for p in per_rank]},
             "device_ms_per_step": round(1e3 * dev_s / args.steps, 3),
             "timing_breakdown_ms": {"sum_of_steps": round(sum(step_wall), 2), "loop": round(1e3 * t_loop, 2), "with_closing_barrier": round(1e3 * wall_a, 2)},
             "e2e": {"value": round(e2e, 2), "unit": "Mpaths/s", "h2d_bytes_per_step": int(h2d / args.steps),
@@ -386,7 +429,7 @@ def main():
                     "call": "ptgpu_anim_frame + ptgpu_set_frame_ranges + ptgpu_render" if args.animation else "ptgpu_render_frame (include/ptgpu.h)"},
             "frame_setup": "ptgpu_set_animation_frame (csrc/frame_setup.cu)" if anim is not None else "snapshot arrays via ptgpu_set_frame",
             "gpu_launches": int(launches),
-            "clocks": sampler.result(),
+            "clocks": clocks_mine,
             # the dominant kernel (wf_trace_cw_kernel), as the contract asks; the whole frame beside it
             "roofline": {"bound": "fp32", "kernel": "wf_trace_cw_kernel",
                          "achieved": round(k_achieved, 3) if k_ok else None, "peak": round(peak_tflops, 2),

@@ -56,6 +56,9 @@ struct CwState
     bool in_blas, any;
     uint32_t cur_inst, subframe;
     Hit hit;
+#ifdef WF_STATS
+    uint32_t n_nodes = 0, n_tris = 0;   // census builds: node tests and triangle tests of this query
+#endif
 };
 
 PT_D uint32_t sign_extend_s8x4(uint32_t x)
@@ -267,6 +270,9 @@ PT_D void cw_test_triangle(const Scene& sc, CwState& st, uint32_t tri)
     const float4* tp = sc.cwtris + 3 * (size_t)tri;
     const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
     float u, v, t; bool bf;
+#ifdef WF_STATS
+    st.n_tris++;
+#endif
     const bool ok = tri_intersect(st.o, st.axis, st.S, mk3(a), mk3(b), mk3(c), u, v, t, bf);
     // The reference accepts strictly closer candidates, so among exactly tied hits (a ray through a
     // shared edge) the first one ITS traversal order finds wins (ray_query.hh:245,289). This kernel
@@ -301,6 +307,9 @@ PT_D void cw_node_phase(const Scene& sc, CwState& st, Stack& stack, const TopLev
         if(st.ngroup.y > 0x00FFFFFFu) stack.set(st.sp++, st.ngroup);
         const uint32_t slot = (child_bit - 24u) ^ (st.oct_inv4 & 0xFFu);
         const uint32_t rel = (uint32_t)__popc(hits_imask & ~(0xFFFFFFFFu << slot));
+#ifdef WF_STATS
+        st.n_nodes++;
+#endif
         cw_intersect_node<TOP>(sc.cwnodes, base + rel, st, st.ngroup, st.tgroup, top);
     }
     else
@@ -346,7 +355,8 @@ PT_D bool cw_pop_phase(const Scene& sc, CwState& st, Stack& stack)
 }
 
 template<bool ANY>
-PT_D bool trace_cw(const Scene& sc, uint32_t subframe, v3 origin, v3 dir, float tmin, float tmax, Hit& hit)
+PT_D bool trace_cw(const Scene& sc, uint32_t subframe, v3 origin, v3 dir, float tmin, float tmax, Hit& hit,
+                   uint32_t* census = nullptr)
 {
     uint2 stack_mem[CW_STACK];
     LocalStack stack{stack_mem};
@@ -369,7 +379,10 @@ PT_D bool trace_cw(const Scene& sc, uint32_t subframe, v3 origin, v3 dir, float 
         if(!cw_pop_phase(sc, st, stack)) break;
     }
     hit = st.hit;
-    return ANY ? hit.t >= 0.0f : hit.t >= 0.0f;
+#ifdef WF_STATS
+    if(census) { census[0] = st.n_nodes; census[1] = st.n_tris; }
+#endif
+    return hit.t >= 0.0f;
 }
 
 struct CwTrav

@@ -588,9 +588,14 @@ __global__ void wf_validate_kernel(Scene sc, RenderJob job, WaveBuffers wb, unsi
         const int sample = job.s_begin + wb.cursor[slot].x * job.s_stride;
         const uint32_t subframe = sample < 0 ? 0u : (uint32_t)sample / (uint32_t)sc.samples_per_subframe;
         Hit h;
+        uint32_t census[2] = {0u, 0u};
+#ifdef WF_STATS
+        struct Flush { unsigned long long* s; uint32_t* c; __device__ ~Flush() {
+            atomicAdd(&s[20], (unsigned long long)c[0]); atomicAdd(&s[21], (unsigned long long)c[1]); atomicAdd(&s[22], 1ull); } } flush{wb.stats, census};
+#endif
         if(shadow)
         {
-            trace_cw<true>(sc, subframe, mk3(fo.x, fo.y, fo.z), mk3(fd.x, fd.y, fd.z), fo.w, PT_MAX_RAY_DIST, h);
+            trace_cw<true>(sc, subframe, mk3(fo.x, fo.y, fo.z), mk3(fd.x, fd.y, fd.z), fo.w, PT_MAX_RAY_DIST, h, census);
             const uint32_t vis = h.t < 0.0f ? 1u : 0u;
             if(vis != wb.visible[slot])
             {
@@ -599,7 +604,7 @@ __global__ void wf_validate_kernel(Scene sc, RenderJob job, WaveBuffers wb, unsi
         }
         else
         {
-            trace_cw<false>(sc, subframe, mk3(fo.x, fo.y, fo.z), mk3(fd.x, fd.y, fd.z), fo.w, PT_MAX_RAY_DIST, h);
+            trace_cw<false>(sc, subframe, mk3(fo.x, fo.y, fo.z), mk3(fd.x, fd.y, fd.z), fo.w, PT_MAX_RAY_DIST, h, census);
             const float4 fh = wb.hit[slot];
             const uint32_t hp = wb.hit_prim[slot];
             if(fh.x != h.t || (h.t >= 0.0f && (__float_as_uint(fh.w) != h.inst || (hp & 0x7FFFFFFFu) != h.prim)))

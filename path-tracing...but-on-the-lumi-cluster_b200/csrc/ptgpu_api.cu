@@ -84,7 +84,10 @@ struct ptgpu_ctx
     int validate = 0;                          // debug: re-trace every ray with the plain traversal and compare
     int max_lanes = 256;                       // wavefront: slots per pixel (power of two)
     size_t pool_budget_bytes = 16ull << 30;    // wavefront: path-state pool budget
-    int tri_threshold = 8, xform_threshold = 4, node_threshold = 16, node_burst = 2;
+    // warp scheduling of wf_trace_cw (-1 = by scene kind: instanced 4 / 2, flat 1 / 3 — with the flat scene
+    // instance entries are rare (the <= 7 per-frame objects), so a lane should not wait for company to enter one,
+    // and longer node bursts pay because no ENTER step competes; profiles/r02_trace_kernel_history.md)
+    int tri_threshold = 8, xform_threshold = -1, node_threshold = 16, node_burst = -1;
     int flat = 1;                              // static instances as one world-space BVH (built at upload)
     int sort = 1;                              // wavefront: bounce and shadow rays sorted by octant + origin cell
     int top_smem = 0;                          // wavefront: top levels of the flat BVH staged in shared memory
@@ -147,7 +150,9 @@ struct ptgpu_ctx
     unsigned long long last_validate_mismatches = 0;
     uint32_t bmp_pitch = 0;
     bool bmp_header_done = false;
-    bool render_pending = false;
+    bool render_pending = false;        // some render was launched (ptgpu_last_render_ms has something to time)
+    bool frame_on_device = false;       // out_bgra / out_bmp hold a full frame (ptgpu_validate_frame, ptgpu_fetch_*)
+    DevBuf<uchar4> rect_bgra;           // ptgpu_render_rect's own image: a rect never overwrites the frame
     int last_launches = 0;
 
     // scratch for the small utility entry points
@@ -265,7 +270,15 @@ int launch_wave(ptgpu_ctx* ctx, const Scene& sc, RenderJob job)
         o_sum = carve(16ull * n_slots), o_cur = carve(8ull * n_slots), o_vis = carve(4ull * n_slots),
         o_qt = carve(4ull * 3ull * (n_slots + 64)), o_qk = carve(4ull * 3ull * (n_slots + 64)), o_qs = carve(4ull * 2ull * (n_slots + 64)),
         o_sh = carve(4ull * 2ull * WF_SORT_BINS), o_st = carve(n_slots), o_qf = carve(4ull * (n_slots + 64)), o_qn = carve(4ull * (n_slots + 64)), o_cnt = carve(sizeof(WaveCounters)), o_stats = carve(40 * 8);
-    if(ctx->wave_mem.reserve(off) != cudaSuccess) return -1;
+    if(ctx->wave_mem.reserve(off) != cudaSuccess)
+    {
+        size_t free_b = 0, total_b = 0;
+        cudaGetLastError();
+        cudaMemGetInfo(&free_b, &total_b);
+        fail(ctx, "the path-state pool of %zu MB (%u slots per pixel) does not fit: %zu MB of device memory free; "
+                  "lower option pool_budget_mb or lanes", off >> 20, lanes, free_b >> 20);
+        return -2;
+    }
     if(!ctx->wave_flag_host)
     {
         if(cudaMallocHost(&ctx->wave_flag_host, 64) != cudaSuccess) return -1;
@@ -286,8 +299,9 @@ int launch_wave(ptgpu_ctx* ctx, const Scene& sc, RenderJob job)
     wb.n_slots = n_slots; wb.seg_cap = n_slots + 64; wb.tiles_x = tiles_x;
     wb.lanes = lanes; wb.lane_shift = lane_shift;
     if(job.min_active < 1) job.min_active = 1;
-    job.tri_threshold = ctx->tri_threshold; job.xform_threshold = ctx->xform_threshold;
-    job.node_threshold = ctx->node_threshold; job.node_burst = ctx->node_burst;
+    const bool flat_scene = sc.flat_root != 0xFFFFFFFFu;
+    job.tri_threshold = ctx->tri_threshold; job.xform_threshold = ctx->xform_threshold > 0 ? ctx->xform_threshold : (flat_scene ? 1 : 4);
+    job.node_threshold = ctx->node_threshold; job.node_burst = ctx->node_burst > 0 ? ctx->node_burst : (flat_scene ? 3 : 2);
 
     cudaStream_t st = ctx->stream;
     int launches = 0;
@@ -325,7 +339,7 @@ int launch_wave(ptgpu_ctx* ctx, const Scene& sc, RenderJob job)
             if(ctx->top_smem) wf_trace_cw_kernel<true><<<sms * WF_CW_BLOCKS, WF_TRACE_THREADS, 0, st>>>(sc, job, wb);
             else wf_trace_cw_kernel<false><<<sms * WF_CW_BLOCKS, WF_TRACE_THREADS, 0, st>>>(sc, job, wb);
             if(timed) cudaEventRecord(ctx->wave_events[4 * rounds + 2], st);
-            if(ctx->validate) wf_validate_kernel<<<sms * 8, 128, 0, st>>>(sc, job, wb, wb.stats);
+            if(ctx->validate) wf_validate_kernel<<<sms * 8, 128, 0, st>>>(sc, job, wb, wb.stats + 39);
             wf_phase_kernel<<<1, 32, 0, st>>>(wb, 1, nullptr);
             wf_classify_kernel<<<sms * 8, 256, 0, st>>>(wb);
             wf_shade_kernel<true><<<sms * WF_SHADE_GRID, 128, 0, st>>>(sc, job, wb);
@@ -346,7 +360,7 @@ int launch_wave(ptgpu_ctx* ctx, const Scene& sc, RenderJob job)
     if(ctx->validate)
     {
         unsigned long long h = 0;
-        cudaMemcpyAsync(&h, wb.stats, sizeof(h), cudaMemcpyDeviceToHost, st);
+        cudaMemcpyAsync(&h, wb.stats + 39, sizeof(h), cudaMemcpyDeviceToHost, st);
         cudaStreamSynchronize(st);
         ctx->last_validate_mismatches = h;
     }
@@ -361,6 +375,9 @@ int launch_wave(ptgpu_ctx* ctx, const Scene& sc, RenderJob job)
                 h[0], h[6], (double)h[1] / h[0], (double)h[2] / h[0], (double)h[3] / h[0], (double)h[4] / h[0], (double)h[5] / h[0],
                 h[8], h[8] ? (double)h[9] / h[8] : 0.0, h[10], h[10] ? (double)h[11] / h[10] : 0.0,
                 h[12], h[12] ? (double)h[13] / h[12] : 0.0, h[12] ? (double)h[14] / h[12] : 0.0, h[12] ? (double)h[15] / h[12] : 0.0);
+        if(h[22]) fprintf(stderr, "WF_STATS plain traversal of the same %llu rays (validate): %.2f node tests, %.2f triangle tests per ray\n",
+                          h[22], (double)h[20] / h[22], (double)h[21] / h[22]);
+        fprintf(stderr, "WF_STATS scheduled kernel per ray-lane: node tests %llu, triangle tests %llu\n", h[1], h[9]);
         fprintf(stderr, "WF_STATS entries by BLAS:");
         for(int i = 0; i < 16; ++i) if(h[24 + i]) fprintf(stderr, " [%d] %llu", i, h[24 + i]);
         fprintf(stderr, "\n");
@@ -388,7 +405,9 @@ int launch_job(ptgpu_ctx* ctx, const RenderJob& job)
     else if(ctx->kernel == 1)
     {
         const int tiles = ((job.w + TILE_W - 1) / TILE_W) * ((job.h + TILE_H - 1) / TILE_H);
-        render_tiles_kernel<WideTrav, false><<<tiles, TILE_THREADS, 0, ctx->stream>>>(sc, job, nullptr);
+        // the straight-line kernel over the plain single-ray traversal of whichever BVH is selected
+        if(ctx->bvh == 1) render_tiles_kernel<CwTrav, false><<<tiles, TILE_THREADS, 0, ctx->stream>>>(sc, job, nullptr);
+        else render_tiles_kernel<WideTrav, false><<<tiles, TILE_THREADS, 0, ctx->stream>>>(sc, job, nullptr);
         launches = 1;
     }
     else if(ctx->kernel == 0)
@@ -399,6 +418,7 @@ int launch_job(ptgpu_ctx* ctx, const RenderJob& job)
     {
         launches = launch_wave(ctx, sc, job);
     }
+    if(launches < 0) return launches;
     if(cudaGetLastError() != cudaSuccess) return -1;
     return launches;
 }
@@ -515,7 +535,7 @@ void ptgpu_destroy(ptgpu_ctx* ctx)
     ctx->pos.release(); ctx->normal.release(); ctx->albedo.release(); ctx->material.release();
     ctx->instances.release(); ctx->wnodes.release(); ctx->wtris.release(); ctx->wblas.release();
     ctx->winst.release(); ctx->wtlas.release(); ctx->cwnodes.release(); ctx->cwtris.release(); ctx->shade_tris.release(); ctx->cw_inst_index.release(); ctx->subframes.release(); ctx->dyn_range.release();
-    ctx->out_bgra.release(); ctx->out_bmp.release(); ctx->out_rgb.release(); ctx->counters.release();
+    ctx->out_bgra.release(); ctx->out_bmp.release(); ctx->out_rgb.release(); ctx->counters.release(); ctx->rect_bgra.release();
     ctx->mega_state.release(); ctx->wave_mem.release(); ctx->wave_flag.release();
     if(ctx->wave_flag_host) cudaFreeHost(ctx->wave_flag_host);
     for(auto& e : ctx->wave_events) cudaEventDestroy(e);
@@ -662,6 +682,7 @@ static int upload_static_common(
     CK(cudaMemcpy(ctx->cw_inst_index.p, w.cw_inst_index.data(), w.cw_inst_index.size() * 4, cudaMemcpyHostToDevice));
     ctx->have_static = true;
     ctx->have_frame = false;
+    ctx->frame_on_device = false;
     return 0;
 }
 
@@ -826,11 +847,13 @@ static int render_full(ptgpu_ctx* ctx, bool bgra, bool bmp)
         launches++;
     }
     int l = launch_job(ctx, job);
+    if(l == -2) return 1;   // launch_wave said why
     if(l < 0) return fail(ctx, "kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     launches += l;
     CK(cudaEventRecord(ctx->ev_end, ctx->stream));
     ctx->last_launches = launches;
     ctx->render_pending = true;
+    ctx->frame_on_device = true;
     return 0;
 }
 
@@ -847,6 +870,7 @@ int ptgpu_sync(ptgpu_ctx* ctx)
 int ptgpu_fetch_bgra(ptgpu_ctx* ctx, uint8_t* out_bgra)
 {
     if(!ctx || !out_bgra) return 1;
+    if(!ctx->frame_on_device) return fail(ctx, "ptgpu_fetch_bgra: no rendered frame on the device");
     if(use(ctx)) return 1;
     CK(cudaMemcpyAsync(out_bgra, ctx->out_bgra.p, (size_t)ctx->cfg.width * ctx->cfg.height * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -861,6 +885,7 @@ size_t ptgpu_bmp_size(const ptgpu_ctx* ctx)
 int ptgpu_fetch_bmp(ptgpu_ctx* ctx, uint8_t* out_bmp)
 {
     if(!ctx || !out_bmp) return 1;
+    if(!ctx->frame_on_device) return fail(ctx, "ptgpu_fetch_bmp: no rendered frame on the device");
     if(use(ctx)) return 1;
     CK(cudaMemcpyAsync(out_bmp, ctx->out_bmp.p, ptgpu_bmp_size(ctx), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -871,7 +896,7 @@ int ptgpu_validate_frame(ptgpu_ctx* ctx, const uint8_t* ref_rgb_half, double* ps
 {
     if(!ctx || !ref_rgb_half || !psnr) return 1;
     if(use(ctx)) return 1;
-    if(!ctx->render_pending) return fail(ctx, "ptgpu_validate_frame: no rendered frame on the device");
+    if(!ctx->frame_on_device) return fail(ctx, "ptgpu_validate_frame: no rendered frame on the device");
     const uint32_t w = (uint32_t)ctx->cfg.width, h = (uint32_t)ctx->cfg.height, hw = (w + 1) / 2, hh = (h + 1) / 2;
     const size_t ref_bytes = (size_t)hw * hh * 3;
     CK(ctx->scratch_a.reserve(ref_bytes + 16));
@@ -943,12 +968,11 @@ int ptgpu_render_rect(
     if(use(ctx)) return 1;
     const size_t npix = (size_t)w * h;
     CK(ctx->out_rgb.reserve(npix * 3));
-    DevBuf<uchar4> tmp_bgra;
     uchar4* d_bgra = nullptr;
     if(out_bgra)
-    {
-        if(npix <= ctx->out_bgra.cap) d_bgra = ctx->out_bgra.p;
-        else { CK(tmp_bgra.reserve(npix)); d_bgra = tmp_bgra.p; }
+    {   // a buffer of its own: the full frame of the last ptgpu_render stays valid for ptgpu_validate_frame / fetch
+        CK(ctx->rect_bgra.reserve(npix));
+        d_bgra = ctx->rect_bgra.p;
     }
     RenderJob job{};
     job.x0 = x0; job.y0 = y0; job.w = w; job.h = h;
@@ -957,13 +981,13 @@ int ptgpu_render_rect(
     job.min_active = ctx->min_active < 0 ? (ctx->kernel == 2 ? 6 : 0) : ctx->min_active;
     CK(cudaEventRecord(ctx->ev_begin, ctx->stream));
     int l = launch_job(ctx, job);
-    if(l < 0) { tmp_bgra.release(); return fail(ctx, "kernel launch failed: %s", cudaGetErrorString(cudaGetLastError())); }
+    if(l == -2) return 1;   // launch_wave said why
+    if(l < 0) return fail(ctx, "kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     CK(cudaEventRecord(ctx->ev_end, ctx->stream));
     ctx->last_launches = l; ctx->render_pending = true;
     if(out_rgb) CK(cudaMemcpyAsync(out_rgb, ctx->out_rgb.p, npix * 12, cudaMemcpyDeviceToHost, ctx->stream));
     if(out_bgra) CK(cudaMemcpyAsync(out_bgra, d_bgra, npix * 4, cudaMemcpyDeviceToHost, ctx->stream));
     cudaError_t e = cudaStreamSynchronize(ctx->stream);
-    tmp_bgra.release();
     if(e != cudaSuccess) return fail(ctx, "render failed: %s", cudaGetErrorString(e));
     return 0;
 }
@@ -1081,9 +1105,9 @@ int ptgpu_set_option(ptgpu_ctx* ctx, const char* key, int64_t value)
     if(!strcmp(key, "kernel")) { if(value < 0 || value > 2) return fail(ctx, "kernel must be 0, 1 or 2"); ctx->kernel = (int)value; return 0; }
     if(!strcmp(key, "bvh")) { if(value != 0 && value != 1) return fail(ctx, "bvh must be 0 or 1"); ctx->bvh = (int)value; return 0; }
     if(!strcmp(key, "tri_threshold")) { if(value < 1 || value > 32) return fail(ctx, "tri_threshold must be 1..32"); ctx->tri_threshold = (int)value; return 0; }
-    if(!strcmp(key, "xform_threshold")) { if(value < 1 || value > 32) return fail(ctx, "xform_threshold must be 1..32"); ctx->xform_threshold = (int)value; return 0; }
+    if(!strcmp(key, "xform_threshold")) { if(value != -1 && (value < 1 || value > 32)) return fail(ctx, "xform_threshold must be 1..32 or -1"); ctx->xform_threshold = (int)value; return 0; }
     if(!strcmp(key, "node_threshold")) { if(value < 1 || value > 32) return fail(ctx, "node_threshold must be 1..32"); ctx->node_threshold = (int)value; return 0; }
-    if(!strcmp(key, "node_burst")) { if(value < 1 || value > 64) return fail(ctx, "node_burst must be 1..64"); ctx->node_burst = (int)value; return 0; }
+    if(!strcmp(key, "node_burst")) { if(value != -1 && (value < 1 || value > 64)) return fail(ctx, "node_burst must be 1..64 or -1"); ctx->node_burst = (int)value; return 0; }
     if(!strcmp(key, "validate")) { ctx->validate = value != 0; return 0; }
     if(!strcmp(key, "flat")) { if(value != 0 && value != 1) return fail(ctx, "flat must be 0 or 1");
         if(value == 1 && ctx->have_static && !ctx->have_flat) return fail(ctx, "flat = 1 must be set before the scene is uploaded (the flat BVH is built at upload)");

@@ -25,6 +25,7 @@
 #include <clocale>
 #include <condition_variable>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <deque>
 #include <mutex>
@@ -64,8 +65,19 @@ static void write_file(const std::string& out_dir, uint frame, const std::vector
     snprintf(name, sizeof(name), "%s/frame_%04u.bmp", out_dir.c_str(), frame); // main.cc:93-101
     FILE* f = fopen(name, "w");
     if(!f) { fprintf(stderr, "Failed to write %s\n", name); exit(1); }
-    fwrite(bmp.data(), 1, bmp.size(), f);
-    fclose(f);
+    // a short write (full disk) must not end in exit code 0 with a truncated frame
+    const bool ok = fwrite(bmp.data(), 1, bmp.size(), f) == bmp.size();
+    if(fclose(f) != 0 || !ok) { fprintf(stderr, "Failed to write %s (short write)\n", name); exit(1); }
+}
+
+// strict non-negative integer argument (atoi would turn "-3" into a huge uint and "x" into 0)
+static bool parse_uint(const char* s, long lo, long hi, long& out)
+{
+    char* end = nullptr;
+    const long v = strtol(s, &end, 10);
+    if(end == s || *end != 0 || v < lo || v > hi) return false;
+    out = v;
+    return true;
 }
 
 int main(int argc, char** argv)
@@ -73,24 +85,58 @@ int main(int argc, char** argv)
     setlocale(LC_ALL, "C"); // main.cc:63
     int gpus = 1;
     uint frame_begin = 0, frame_end = 0, frame_step = 1;
-    std::string out_dir = "output";
+    std::string out_dir = "output", dump_dir;
     bool write_files = true, serial = false;
     for(int i = 1; i < argc; ++i)
     {
-        if(!strcmp(argv[i], "--gpus") && i + 1 < argc) gpus = atoi(argv[++i]);
-        else if(!strcmp(argv[i], "--frames") && i + 2 < argc) { frame_begin = atoi(argv[++i]); frame_end = atoi(argv[++i]); }
-        else if(!strcmp(argv[i], "--step") && i + 1 < argc) frame_step = atoi(argv[++i]);
+        long v = 0, w = 0;
+        if(!strcmp(argv[i], "--gpus") && i + 1 < argc && parse_uint(argv[i + 1], 1, 1024, v)) { gpus = (int)v; ++i; }
+        else if(!strcmp(argv[i], "--frames") && i + 2 < argc && parse_uint(argv[i + 1], 0, 1 << 30, v) && parse_uint(argv[i + 2], v + 1, 1 << 30, w))
+        { frame_begin = (uint)v; frame_end = (uint)w; i += 2; }
+        else if(!strcmp(argv[i], "--step") && i + 1 < argc && parse_uint(argv[i + 1], 1, 1 << 30, v)) { frame_step = (uint)v; ++i; }
         else if(!strcmp(argv[i], "--out") && i + 1 < argc) out_dir = argv[++i];
+        else if(!strcmp(argv[i], "--dump") && i + 1 < argc) dump_dir = argv[++i];
         else if(!strcmp(argv[i], "--no-write")) write_files = false;
         else if(!strcmp(argv[i], "--serial")) serial = true;
-        else { fprintf(stderr, "usage: %s [--gpus N] [--frames BEGIN END] [--step S] [--out DIR] [--no-write] [--serial]\n", argv[0]); return 2; }
+        else { fprintf(stderr, "usage: %s [--gpus N>=1] [--frames BEGIN END (BEGIN < END)] [--step S>=1] [--out DIR] [--dump DIR] [--no-write] [--serial]\n", argv[0]); return 2; }
     }
 
     double t0 = now_s();
     scene loaded = load_scene();
     printf("EXECUTION TIME OF load_scene() : %.0fms\n", 1e3 * (now_s() - t0));
     if(frame_end == 0) frame_end = get_animation_frame_count(loaded); // main.cc:74 as intended
-    if(frame_step == 0) frame_step = 1;
+
+    if(!dump_dir.empty())
+    {   // test hook: the arrays this program hands to the C ABI (main.cc:29-37), so that another host can
+        // push exactly the same inputs through the library and compare the frames byte for byte
+        auto put = [&](const std::string& name, const void* p, size_t bytes) {
+            FILE* f = fopen((dump_dir + "/" + name).c_str(), "w");
+            if(!f || fwrite(p, 1, bytes, f) != bytes || fclose(f) != 0) { fprintf(stderr, "Failed to write %s\n", name.c_str()); exit(1); }
+        };
+        scene s = loaded;
+        for(uint frame = frame_begin; frame < frame_end; frame += frame_step)
+        {
+            setup_animation_frame(s, frame);
+            const size_t n_static_nodes = s.subframes[0].tlas.node_offset, n_static = s.static_instance_count;
+            if(frame == frame_begin)
+            {
+                put("nodes.bin", s.bvh_buf.nodes.data(), n_static_nodes * sizeof(bvh_node));
+                put("links.bin", s.bvh_buf.links.data(), 8 * n_static_nodes * sizeof(bvh_link));
+                put("indices.bin", s.mesh_buf.indices.data(), s.mesh_buf.indices.size() * 4);
+                put("pos.bin", s.mesh_buf.pos.data(), s.mesh_buf.pos.size() * sizeof(float3));
+                put("normal.bin", s.mesh_buf.normal.data(), s.mesh_buf.normal.size() * sizeof(float3));
+                put("albedo.bin", s.mesh_buf.albedo.data(), s.mesh_buf.albedo.size() * sizeof(float4));
+                put("material.bin", s.mesh_buf.material.data(), s.mesh_buf.material.size() * sizeof(float4));
+                put("instances.bin", s.instances.data(), n_static * sizeof(tlas_instance));
+            }
+            char pre[64];
+            snprintf(pre, sizeof(pre), "frame_%04u_", frame);
+            put(std::string(pre) + "subframes.bin", s.subframes.data(), s.subframes.size() * sizeof(subframe));
+            put(std::string(pre) + "dyn_instances.bin", s.instances.data() + n_static, (s.instances.size() - n_static) * sizeof(tlas_instance));
+            put(std::string(pre) + "tlas_nodes.bin", s.bvh_buf.nodes.data() + n_static_nodes, (s.bvh_buf.nodes.size() - n_static_nodes) * sizeof(bvh_node));
+            put(std::string(pre) + "tlas_links.bin", s.bvh_buf.links.data() + 8 * n_static_nodes, (s.bvh_buf.links.size() - 8 * n_static_nodes) * sizeof(bvh_link));
+        }
+    }
 
     ptgpu_config cfg;
     cfg.width = IMAGE_WIDTH; cfg.height = IMAGE_HEIGHT; cfg.spp = SAMPLES_PER_PIXEL; cfg.max_bounces = MAX_BOUNCES;

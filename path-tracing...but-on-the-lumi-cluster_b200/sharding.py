@@ -18,12 +18,17 @@ def strided_frames(n_frames, rank, world, begin=0, step=1):
     return list(range(begin + step * rank, n_frames, step * world))
 
 
-def bench_frame(step, rank, world, available):
-    """Snapshot frame rendered by `rank` at benchmark step `step` (bench.py): consecutive global
-    work items (step*world + rank) cycle through the available snapshot frames."""
+def bench_frame(step, rank, steps, available):
+    """Snapshot frame rendered by `rank` at benchmark step `step` of `steps` (bench.py). The run's frame
+    list is available[j % len] for j < steps; rank r walks it rotated by r. Every rank therefore renders the
+    same MULTISET of frames whatever the rank count, so throughput ratios between rank counts measure
+    scaling and not the frame mix (per-frame cost varies ~5x over the animation), while at any moment
+    the ranks render different frames."""
     if not available:
         raise ValueError("no snapshot frames")
-    return available[(step * world + rank) % len(available)]
+    if steps < 1:
+        raise ValueError("steps must be >= 1")
+    return available[((step + rank) % steps) % len(available)]
 
 
 def check_partition(assignments, n_frames, begin=0, step=1):

@@ -20,9 +20,9 @@ rank, world = dist.get_rank(), dist.get_world_size()
 mine = sh.strided_frames(1800, rank, world)
 gathered = [None] * world
 dist.all_gather_object(gathered, mine)
-# the bench's per-step frame choice: consecutive global work items, no frame rendered twice per pass
+# the bench's per-step frame choice: the same 20-frame list on every rank, rotated by the rank
 avail = list(range(14))
-steps = [sh.bench_frame(s, rank, world, avail) for s in range(7)]
+steps = [sh.bench_frame(s, rank, 20, avail) for s in range(20)]
 all_steps = [None] * world
 dist.all_gather_object(all_steps, steps)
 # timing protocol of bench.py: max over ranks of the per-rank wall time, sum of work
@@ -32,7 +32,7 @@ w = torch.tensor([float(len(mine))], dtype=torch.float64)
 dist.all_reduce(w, op=dist.ReduceOp.SUM)
 if rank == 0:
     print(json.dumps({"ok": sh.check_partition(gathered, 1800), "tmax": t.item(), "frames": w.item(),
-                      "steps": sorted(f for s in all_steps for f in s)}))
+                      "steps": [sorted(s) for s in all_steps], "order": all_steps}))
 dist.destroy_process_group()
 """
 
@@ -70,4 +70,18 @@ def test_world_size_2_gloo(tmp_path):
     res = json.loads(line)
     assert res["ok"] is True
     assert res["tmax"] == 2.0 and res["frames"] == 1800.0
-    assert res["steps"] == list(range(14))   # 2 ranks x 7 steps cover the 14 snapshots once
+    want = sorted([j % 14 for j in range(20)])
+    assert res["steps"] == [want, want]            # both ranks render the same multiset of frames ...
+    assert res["order"][0] != res["order"][1]      # ... in a different order (rotated by the rank)
+
+
+def test_bench_frame_multisets(pkg):
+    sh = pkg.sharding
+    avail = [0, 100, 200, 330, 420, 520, 660, 800, 1000, 1100, 1250, 1400, 1600, 1750]
+    for steps in (1, 3, 14, 20, 33):
+        ref = sorted(sh.bench_frame(i, 0, steps, avail) for i in range(steps))
+        for world in (2, 4, 8):
+            for rank in range(world):
+                assert sorted(sh.bench_frame(i, rank, steps, avail) for i in range(steps)) == ref
+    with pytest.raises(ValueError):
+        sh.bench_frame(0, 0, 0, avail)

@@ -100,8 +100,10 @@ def test_film_offset(renderer, oracle):
     u[:8] = [[0, 0], [0.5, 0.5], [1 - 2 ** -24, 0.25], [2 ** -32, 0.75], [0.999, 0.999], [1e-6, 1e-6], [0.5, 0], [0, 0.5]]
     got, want = both(renderer, oracle, "FILM_OFFSET", u)
     assert np.isfinite(got[:, :2]).all()
+    # inv_erf is steep at the ends of the unit interval: the last ulps of u move the offset by 1e-4 pixel there
     err = np.abs(got[:, :2] - want[:, :2]).max(axis=1)
-    bar("film_abs", err.max())
+    bar("film_p999", np.percentile(err, 99.9))
+    bar("film_max", err.max())
 
 
 @pytest.mark.parametrize("frame", [330, 520])
@@ -169,12 +171,24 @@ def test_sample_bsdf_every_lobe(renderer, oracle):
     # u.z within rounding of a lobe boundary may pick the other lobe (the reference's probabilities are double)
     assert (~same).sum() <= 4, (~same).sum()
     err_dir = np.abs(got[same, 0:3] - want[same, 0:3]).max(axis=1)
-    err_att = rel_err(got[same, 3:6], want[same, 3:6], floor=1e-4)
-    err_pdf = rel_err(got[same, 6:7], want[same, 6:7], floor=1e-4)
     bar("sample_dir_p999", np.percentile(err_dir, 99.9))
     bar("sample_dir_max", err_dir.max())
-    bar("sample_att_p999", np.percentile(err_att, 99.9))
-    bar("sample_pdf_p999", np.percentile(err_pdf, 99.9))
+    # What the path tracer multiplies into the throughput is attenuation / |pdf| (path_tracer.hh:725-732): that
+    # ratio is well conditioned and must agree tightly. The two factors on their own carry the GGX density,
+    # which at roughness 0.002 (just above the delta threshold) is a ratio of nearly cancelling terms,
+    # a^2 / (h.z^2 (a^2 - 1) + 1)^2 with 1 - h.z^2 ~ a^2: the last ulp of h.z moves it by percents, and the
+    # reference evaluates part of it in double ("double-precision leakage").
+    g, w = got[same], want[same]
+    ok = ~((w[:, 3:6] == 0).all(axis=1))
+    weight_g = g[ok, 3:6] / np.abs(g[ok, 6:7])
+    weight_w = w[ok, 3:6] / np.abs(w[ok, 6:7])
+    bar("sample_weight_p999", np.percentile(rel_err(weight_g, weight_w, floor=1e-4), 99.9))
+    ill = inp[same, 9] < 0.005
+    err_att = rel_err(g[:, 3:6], w[:, 3:6], floor=1e-4)
+    err_pdf = rel_err(g[:, 6:7], w[:, 6:7], floor=1e-4)
+    bar("sample_att_p999", np.percentile(err_att[~ill], 99.9))
+    bar("sample_pdf_p999", np.percentile(err_pdf[~ill], 99.9))
+    bar("sample_pdf_ill_max", err_pdf[ill].max())
     tir = (inp[:2000, 12] == 1.5) & (lw[:2000] == 0)
     assert tir.sum() > 50                                      # total internal reflection happened and was "bad" on both sides
     assert (lg[:2000][tir] == 0).all()
@@ -291,16 +305,16 @@ def test_trace_shadow_ray(frames, oracle, frame):
     # bounded tmax: nothing beyond it counts
     inp[:, 7] = 1e-3
     got, want = both(r, oracle, "SHADOW_RAY", inp)
-    assert (got[:, 0] == want[:, 0]).mean() > 0.995
+    bar("shadow_short_agree", (got[:, 0] == want[:, 0]).mean(), greater=True)
 
 
 # bars: about twice the error measured on B200 (printed by `python tests/test_subfunctions_gpu.py`)
 BARS = {
-    "film_abs": 5e-5, "camera_dir": 1e-5, "camera_origin_abs": 2e-5, "vndf": 2e-5,
-    "bsdf_p999": 1e-3, "bsdf_max": 5e-2,
-    "sample_dir_p999": 1e-4, "sample_dir_max": 1e-2, "sample_att_p999": 1e-3, "sample_pdf_p999": 1e-3,
-    "cone_abs": 1e-5, "sky_att_p995": 1e-3, "sky_scat_att_p995": 1e-3, "sky_scat_p995": 2e-3,
-    "hit_pos_abs": 5e-2, "hit_material_p99": 5e-3, "hit_normal_p99": 5e-3, "shadow_agree": 0.99,
+    "film_p999": 2e-4, "film_max": 1e-3, "camera_dir": 2e-6, "camera_origin_abs": 1e-5, "vndf": 3e-5,
+    "bsdf_p999": 1e-4, "bsdf_max": 5e-3,
+    "sample_dir_p999": 5e-6, "sample_dir_max": 2e-4, "sample_att_p999": 1e-3, "sample_pdf_p999": 1e-3, "sample_weight_p999": 1e-4, "sample_pdf_ill_max": 0.3,
+    "cone_abs": 5e-5, "sky_att_p995": 5e-4, "sky_scat_att_p995": 3e-4, "sky_scat_p995": 6e-4,
+    "hit_pos_abs": 2e-4, "hit_material_p99": 1e-6, "hit_normal_p99": 1.5e-3, "shadow_agree": 0.995, "shadow_short_agree": 0.99,
 }
 
 
@@ -308,7 +322,8 @@ if __name__ == "__main__":
     # prints the measured errors beside the bars (run on a GPU box; bars are not enforced here)
     import __graft_entry__ as ge
     from oracle import refbind
-    from tests.conftest import FrameCache
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from conftest import FrameCache
     pkg = ge.load_package()
     o = refbind.get("fast")
     o.load_scene()
@@ -328,3 +343,21 @@ if __name__ == "__main__":
                 print("%-40s %-5s ASSERT %s" % (name, p, str(e)[:300]))
     for k, v in MEASURED.items():
         print("%-22s bar %-8g measured %s" % (k, BARS[k], " ".join("%.3g" % x for x in v)))
+    # where sample_bsdf's attenuation differs most: inputs and both outputs, by lobe
+    rng = np.random.RandomState(15)
+    n = 40000
+    sf = surfaces(rng, n)
+    inp = np.column_stack([rng.uniform(0, 1, (n, 3)), view_dirs(rng, n), sf]).astype(np.float32)
+    got, want = both(rr, o, "SAMPLE_BSDF", inp)
+    lw = lobe_of(want, inp[:, 9])
+    err = rel_err(got[:, 3:6], want[:, 3:6], floor=1e-4)
+    for lobe in range(5):
+        m = lw == lobe
+        if m.any():
+            print("lobe %d: n %d, attenuation rel err p50 %.2e p99 %.2e p99.9 %.2e max %.2e" % (
+                lobe, m.sum(), np.percentile(err[m], 50), np.percentile(err[m], 99), np.percentile(err[m], 99.9), err[m].max()))
+    np.set_printoptions(precision=7, suppress=False, linewidth=200)
+    for i in np.argsort(-err)[:12]:
+        print("row %d lobe %d err %.3e\n  in  u %s view %s albedo %s rough %.4g metal %.3g trans %.3g eta %.4g\n  gpu dir %s att %s pdf %.6g\n  ref dir %s att %s pdf %.6g" % (
+            i, lw[i], err[i], inp[i, 0:3], inp[i, 3:6], inp[i, 6:9], inp[i, 9], inp[i, 10], inp[i, 11], inp[i, 12],
+            got[i, 0:3], got[i, 3:6], got[i, 6], want[i, 0:3], want[i, 3:6], want[i, 6]))
