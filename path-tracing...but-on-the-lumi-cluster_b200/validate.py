@@ -131,47 +131,70 @@ def validate_frame(ref_img, own_img):
     return p, p >= ACCEPT_MIN_PSNR
 
 
+class FrameVerdict:
+    """One line of the report: a frame that is missing, or its PSNR and whether it passes."""
+
+    def __init__(self, index, psnr_db=None):
+        self.index = index
+        self.psnr = psnr_db
+        self.missing = psnr_db is None
+        self.good = (not self.missing) and psnr_db >= ACCEPT_MIN_PSNR
+
+    def line(self):
+        # the strings are the reference tool's output format (validator.py:31-54): other scripts parse them
+        name = str(self.index).zfill(4)
+        if self.missing:
+            return name + ": (missing image)"
+        return name + ": " + str(self.psnr) + (" GOOD" if self.good else " BAD, BROKEN IMAGE?")
+
+
+def validate_directory(ref_dir, own_dir, frame_count=FRAME_COUNT):
+    """Verdicts for frames 0 .. frame_count-1 of `own_dir` (frame_NNNN.bmp) against `ref_dir` (NNNN.png).
+    Raises FileNotFoundError naming the first reference image that does not exist."""
+    for i in range(frame_count):
+        ref = os.path.join(ref_dir, "%04d.png" % i)
+        if not os.path.exists(ref):
+            raise FileNotFoundError(ref_dir + "/" + "%04d.png" % i)
+    verdicts = []
+    for i in range(frame_count):
+        own = os.path.join(own_dir, "frame_%04d.bmp" % i)
+        if not os.path.exists(own):
+            verdicts.append(FrameVerdict(i))
+        else:
+            verdicts.append(FrameVerdict(i, validate_frame(read_png(os.path.join(ref_dir, "%04d.png" % i)), read_bmp(own))[0]))
+    return verdicts
+
+
+def summary(verdicts):
+    """The closing block of the report (validator.py:58-66)."""
+    scored = [v.psnr for v in verdicts if not v.missing]
+    ok = all(v.good for v in verdicts)
+    return ("Validation result: " + ("successful" if ok else "failure") + ".\n" +
+            "Sum PSNR: " + str(sum(scored) if scored else 0) + "\n" +
+            "Min PSNR: " + str(min(scored) if scored else 1000) + "\n" +
+            "Max PSNR: " + str(max(scored) if scored else 0) + "\n")
+
+
 def main(argv=None, frame_count=FRAME_COUNT, out=sys.stdout):
+    """Command line of the reference's validator.py: prints one line per frame and the summary, writes
+    validation_result.txt, returns True / False (None when the run could not start)."""
     argv = sys.argv if argv is None else argv
     if len(argv) != 3:
         print("Usage: " + argv[0] + " reference_directory own_directory", file=out)
-        return
-    ref_path, own_path = argv[1], argv[2]
-    validation_str, success = "", True
-    sum_psnr, min_psnr, max_psnr = 0, 1000, 0
-    for i in range(frame_count):
-        frame_name = str(i).zfill(4)
-        ref_img_path = ref_path + "/" + frame_name + ".png"
-        own_img_path = own_path + "/frame_" + frame_name + ".bmp"
-        report = frame_name + ": "
-        if not os.path.exists(ref_img_path):
-            print("Reference files are incomplete, quitting!!!", file=out)
-            print(ref_img_path + " is missing.", file=out)
-            return
-        if not os.path.exists(own_img_path):
-            report += "(missing image)"
-            success = False
-        else:
-            p, good = validate_frame(read_png(ref_img_path), read_bmp(own_img_path))
-            sum_psnr += p
-            min_psnr = min(min_psnr, p)
-            max_psnr = max(max_psnr, p)
-            report += str(p)
-            if not good:
-                success = False
-                report += " BAD, BROKEN IMAGE?"
-            else:
-                report += " GOOD"
-        validation_str += report + "\n"
-        print(report, file=out)
-    outcome_str = "Validation result: successful.\n" if success else "Validation result: failure.\n"
-    outcome_str += "Sum PSNR: " + str(sum_psnr) + "\n"
-    outcome_str += "Min PSNR: " + str(min_psnr) + "\n"
-    outcome_str += "Max PSNR: " + str(max_psnr) + "\n"
-    print(outcome_str, file=out)
-    with open("validation_result.txt", "w") as text_file:
-        text_file.write(validation_str + outcome_str)
-    return success
+        return None
+    try:
+        verdicts = validate_directory(argv[1], argv[2], frame_count)
+    except FileNotFoundError as e:
+        print("Reference files are incomplete, quitting!!!", file=out)
+        print(str(e) + " is missing.", file=out)
+        return None
+    body = "".join(v.line() + "\n" for v in verdicts)
+    tail = summary(verdicts)
+    out.write(body)
+    print(tail, file=out)
+    with open("validation_result.txt", "w") as f:
+        f.write(body + tail)
+    return all(v.good for v in verdicts)
 
 
 if __name__ == "__main__":

@@ -312,7 +312,7 @@ def test_trace_shadow_ray(frames, oracle, frame):
 BARS = {
     "film_p999": 2e-4, "film_max": 1e-3, "camera_dir": 2e-6, "camera_origin_abs": 1e-5, "vndf": 3e-5,
     "bsdf_p999": 1e-4, "bsdf_max": 5e-3,
-    "sample_dir_p999": 5e-6, "sample_dir_max": 2e-4, "sample_att_p999": 1e-3, "sample_pdf_p999": 1e-3, "sample_weight_p999": 1e-4, "sample_pdf_ill_max": 0.3,
+    "sample_dir_p999": 5e-6, "sample_dir_max": 2e-4, "sample_att_p999": 1e-3, "sample_pdf_p999": 1e-3, "sample_weight_p999": 3e-4, "sample_pdf_ill_max": 0.3,
     "cone_abs": 5e-5, "sky_att_p995": 5e-4, "sky_scat_att_p995": 3e-4, "sky_scat_p995": 6e-4,
     "hit_pos_abs": 2e-4, "hit_material_p99": 1e-6, "hit_normal_p99": 1.5e-3, "shadow_agree": 0.995, "shadow_short_agree": 0.99,
 }
