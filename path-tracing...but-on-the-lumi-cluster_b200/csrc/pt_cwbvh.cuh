@@ -93,9 +93,12 @@ PT_D void cw_set_space(CwState& st, v3 o, v3 d)
     st.oct_inv4 = oct * 0x01010101u;
 }
 
-// Byte j of w as a float: I2F.U8 (XU pipe). An exact ALU+FMA-pipe form (PRMT builds 2^23 + b, one FADD
-// removes the 2^23) measured 1.4-6 % slower: the kernel is bound by issue slots, not by the XU pipe, and that
-// form costs one more instruction per byte (profiles/r01_trace_kernel_history.md).
+// Byte j of w as a float: I2F.U8 (XU pipe, 60-66 % busy in wf_trace_cw). Measured alternatives, all slower
+// (profiles/r01_trace_kernel_history.md, r02_trace_kernel_history.md): the exact ALU+FMA form (PRMT builds
+// 2^23 + b, one FADD removes the 2^23: one more instruction per byte, +1.4-6 %); the same with the 2^23
+// folded into the slab offset (no extra instruction, boxes stored one cell larger because the folded offset
+// rounds to half a cell: +4-6 %, the ALU pipe takes the load and spills grow). The kernel is bound by issue
+// slots; the XU pipe is busy but not the limiter.
 PT_D float u8f(uint32_t w, int j) { return (float)((w >> (8 * j)) & 0xFFu); }
 
 // Top levels of the flat BVH staged in shared memory (north_star: "staging the top levels in shared memory
