@@ -94,6 +94,10 @@ void ptgpu_default_config(ptgpu_config* cfg);
 /* Creates a context on CUDA device `device`. Fails (non-zero) if no sm_100 device is present:
  * there is no CPU fallback. On failure *out is NULL and ptgpu_last_error(NULL) has the text. */
 int ptgpu_create(ptgpu_ctx** out, int device, const ptgpu_config* cfg);
+/* Creates the CUDA context of `device` ahead of ptgpu_create (about a second per GPU on an 8-GPU box, serialised
+ * by the driver): a multi-GPU host calls it from one thread per GPU at program start and loads its scene
+ * meanwhile. Optional; 0 = ok. */
+int ptgpu_warm_up(int device);
 void ptgpu_destroy(ptgpu_ctx* ctx);
 const char* ptgpu_last_error(const ptgpu_ctx* ctx);
 
@@ -379,6 +383,18 @@ int ptgpu_host_flat_check(
     const ptgpu_bvh_node* nodes, size_t n_nodes, const ptgpu_bvh_link* links, size_t n_links,
     const uint32_t* indices, size_t n_indices, const ptgpu_float3* pos, size_t n_verts,
     const ptgpu_tlas_instance* instances, size_t n_static, uint64_t out[8], char* err, size_t err_len);
+/* Host-only, needs no GPU and no context: does the CPU work of ptgpu_upload_static (BVH flattening and, with
+ * flat != 0, the flat static scene: seconds for the shipped scene) and keeps the result in the process-wide
+ * cache, where every later ptgpu_upload_static of the same arrays finds it. A multi-GPU driver calls it right
+ * after load_scene(), while its worker threads are still creating their CUDA contexts. */
+int ptgpu_host_prepare_static(
+    const ptgpu_bvh_node* nodes, size_t n_nodes, const ptgpu_bvh_link* links, size_t n_links,
+    const uint32_t* indices, size_t n_indices, const ptgpu_float3* pos, size_t n_verts,
+    const ptgpu_tlas_instance* instances, size_t n_static, int32_t flat, char* err, size_t err_len);
+/* Host-only: the check ptgpu_set_frame_ranges applies to the per-subframe dynamic sets (ranges inside
+ * [0, n_dyn], at most PTGPU_MAX_DYNAMIC_PER_SUBFRAME instances per subframe). 0 = accepted. */
+int ptgpu_host_check_dynamic_ranges(const uint32_t* dyn_begin, const uint32_t* dyn_end, size_t n_subframes, size_t n_dyn,
+                                    char* err, size_t err_len);
 /* The same for ptgpu_upload_meshes' own BLAS builder. */
 int ptgpu_host_build_check(
     const uint32_t* indices, size_t n_indices, const ptgpu_float3* pos, size_t n_verts,

@@ -24,6 +24,25 @@ inline void die(ptgpu_ctx* ctx, const char* what)
     std::exit(1);
 }
 
+// The CPU half of the static-scene upload (BVH flattening, flat static scene), done once for all workers of the
+// process: call after load_scene(); every renderer<Scene>::set_frame then finds the result cached.
+template<class Scene>
+inline void prepare_static(const Scene& s)
+{
+    const size_t n_static_nodes = s.bvh_buf.nodes.size();   // before any setup_animation_frame: BLAS nodes only
+    char err[512];
+    if(ptgpu_host_prepare_static(
+           reinterpret_cast<const ptgpu_bvh_node*>(s.bvh_buf.nodes.data()), n_static_nodes,
+           reinterpret_cast<const ptgpu_bvh_link*>(s.bvh_buf.links.data()), 8 * n_static_nodes,
+           s.mesh_buf.indices.data(), s.mesh_buf.indices.size(),
+           reinterpret_cast<const ptgpu_float3*>(s.mesh_buf.pos.data()), s.mesh_buf.pos.size(),
+           reinterpret_cast<const ptgpu_tlas_instance*>(s.instances.data()), s.static_instance_count, 1, err, sizeof(err)) != 0)
+    {
+        std::fprintf(stderr, "ptgpu_host_prepare_static: %s\n", err);
+        std::exit(1);
+    }
+}
+
 // One GPU worker bound to one `scene` object (scene.hh:40-65). The static part is uploaded on the
 // first frame; it must not change afterwards (load_scene() runs once, main.cc:67).
 template<class Scene>

@@ -16,7 +16,7 @@ SYMBOLS = [
     "ptgpu_pcg4d", "ptgpu_render_async", "ptgpu_fetch_bgra", "ptgpu_fetch_bmp", "ptgpu_sync",
     "ptgpu_last_render_ms", "ptgpu_set_option", "ptgpu_read_counters", "ptgpu_scene_stats",
     "ptgpu_host_flatten_check", "ptgpu_get_stat", "ptgpu_validate_frame",
-    "ptgpu_upload_meshes", "ptgpu_host_build_check", "ptgpu_host_flat_check", "ptgpu_debug_eval",
+    "ptgpu_upload_meshes", "ptgpu_host_build_check", "ptgpu_host_flat_check", "ptgpu_debug_eval", "ptgpu_host_check_dynamic_ranges", "ptgpu_host_prepare_static", "ptgpu_warm_up",
     "ptgpu_meshes_create", "ptgpu_meshes_destroy", "ptgpu_meshes_last_error", "ptgpu_meshes_load_obj",
     "ptgpu_meshes_index_count", "ptgpu_meshes_vertex_count", "ptgpu_meshes_indices", "ptgpu_meshes_pos",
     "ptgpu_meshes_normal", "ptgpu_meshes_albedo", "ptgpu_meshes_material",
@@ -113,6 +113,9 @@ def load_library():
     L.ptgpu_set_animation_frame.argtypes = [vp, vp, C.c_uint32]
     L.ptgpu_get_stat.argtypes = [vp, C.c_char_p, C.POINTER(C.c_uint64)]
     L.ptgpu_host_flatten_check.argtypes = [vp, sz, vp, sz, vp, sz, vp, sz, vp, sz, C.POINTER(C.c_uint64), C.c_char_p, sz]
+    L.ptgpu_warm_up.argtypes = [C.c_int]
+    L.ptgpu_host_prepare_static.argtypes = [vp, sz, vp, sz, vp, sz, vp, sz, vp, sz, C.c_int32, C.c_char_p, sz]
+    L.ptgpu_host_check_dynamic_ranges.argtypes = [vp, vp, sz, sz, C.c_char_p, sz]
     L.ptgpu_debug_eval.argtypes = [vp, C.c_int32, vp, sz, vp]
     L.ptgpu_host_flat_check.argtypes = [vp, sz, vp, sz, vp, sz, vp, sz, vp, sz, C.POINTER(C.c_uint64), C.c_char_p, sz]
     L.ptgpu_upload_meshes.argtypes = [vp, vp, sz, vp, vp, vp, vp, sz, vp, sz, vp, sz]

@@ -61,8 +61,50 @@ uint64_t hash_bytes(uint64_t h, const void* p, size_t n)
     for(size_t i = 0; i < (n & 7); ++i) { h ^= b[i]; h *= 0x100000001B3ull; }
     return h;
 }
-std::mutex g_flat_mutex;
-std::map<uint64_t, std::shared_ptr<const FlatScene>> g_flat_cache;
+// Host side of an uploaded static scene: the compressed BVHs of the meshes (+ static TLAS) and, with option
+// "flat", the flat static scene. Built once per process and set of input arrays.
+struct HostScene
+{
+    WideScene wide;
+    FlatScene flat;
+    bool have_flat = false;
+};
+std::mutex g_scene_mutex;
+std::map<uint64_t, std::shared_ptr<const HostScene>> g_scene_cache;
+
+std::shared_ptr<const HostScene> get_host_scene(
+    const ptgpu_bvh_node* nodes, size_t n_nodes, const ptgpu_bvh_link* links, size_t n_links,
+    const uint32_t* indices, size_t n_indices, const ptgpu_float3* pos, size_t n_verts,
+    const ptgpu_tlas_instance* instances, size_t n_static, const ptgpu_mesh* meshes, size_t n_meshes,
+    bool want_flat, std::string& err)
+{
+    uint64_t h = 0xCBF29CE484222325ull;
+    if(nodes) { h = hash_bytes(h, nodes, n_nodes * sizeof(ptgpu_bvh_node)); h = hash_bytes(h, links, n_links * sizeof(ptgpu_bvh_link)); }
+    if(meshes) h = hash_bytes(h, meshes, n_meshes * sizeof(ptgpu_mesh));
+    h = hash_bytes(h, instances, n_static * sizeof(ptgpu_tlas_instance));
+    h = hash_bytes(h, indices, n_indices * 4);
+    h = hash_bytes(h, pos, n_verts * sizeof(ptgpu_float3));
+    const uint64_t flag = want_flat ? 1 : 0;
+    h = hash_bytes(h, &flag, 8);
+    std::lock_guard<std::mutex> lock(g_scene_mutex);   // a second context waits for the first one's build
+    auto it = g_scene_cache.find(h);
+    if(it != g_scene_cache.end()) return it->second;
+    auto hs = std::make_shared<HostScene>();
+    if(!build_wide_scene(nodes, n_nodes, links, indices, n_indices, pos, n_verts, instances, n_static, hs->wide, err, meshes, n_meshes))
+    { err = "wide BVH build failed: " + err; return nullptr; }
+    if(want_flat)
+    {
+        const uint32_t node_base = (uint32_t)(hs->wide.cw_nodes.size() / 5), tri_base = (uint32_t)(hs->wide.cw_tris.size() / 3);
+        if(!build_flat_scene(hs->wide, indices, pos, instances, n_static, node_base, tri_base, hs->flat, err))
+        { err = "flat scene build failed: " + err; return nullptr; }
+        if(2 * hs->flat.depth + 8 > (uint32_t)CW_STACK)
+        { err = "flat scene: BVH depth " + std::to_string(hs->flat.depth) + " needs a deeper traversal stack than CW_STACK"; return nullptr; }
+        hs->have_flat = true;
+    }
+    if(g_scene_cache.size() >= 3) g_scene_cache.erase(g_scene_cache.begin());
+    g_scene_cache[h] = hs;
+    return hs;
+}
 
 } // namespace
 
@@ -106,7 +148,7 @@ struct ptgpu_ctx
     std::vector<ptgpu_tlas_instance> host_static; // kept for the wide instance records
 
     // wide layout
-    WideScene wide_host;            // host-side build result (node/tri arrays, blas table)
+    std::shared_ptr<const HostScene> host;   // host-side build results (shared by the contexts of a process)
     DevBuf<WideNode> wnodes;
     DevBuf<float4> wtris;
     DevBuf<WideBlas> wblas;
@@ -204,7 +246,7 @@ Scene make_scene(ptgpu_ctx* ctx)
     s.wnodes = ctx->wnodes.p; s.wtris = ctx->wtris.p; s.wblas = ctx->wblas.p; s.winst = ctx->winst.p;
     s.wtlas = ctx->wtlas.p; s.dyn_range = ctx->dyn_range.p;
     s.cwnodes = ctx->cwnodes.p; s.cwtris = ctx->cwtris.p; s.cw_inst_index = ctx->cw_inst_index.p;
-    s.cw_tlas_root = ctx->wide_host.cw_tlas_root;
+    s.cw_tlas_root = ctx->host ? ctx->host->wide.cw_tlas_root : 0u;
     s.flat_root = ctx->flat && ctx->have_flat ? ctx->flat_root : 0xFFFFFFFFu;
     s.flat_top = ctx->flat_top;
     s.dyn_first = (uint32_t)ctx->dyn_first;
@@ -423,6 +465,34 @@ int launch_job(ptgpu_ctx* ctx, const RenderJob& job)
     return launches;
 }
 
+// Per-subframe dynamic instance sets -> the kernels' encoding {prefix p, a | len << 20}: ids [n_static,
+// n_static + p) are seen by every subframe (frame-static extras: logo, buddha), ids n_static + [a, a + len) by
+// this one. The kernels keep a subframe's set as one 24-bit group / 16 stack entries: more is refused here.
+bool encode_dynamic_ranges(const uint32_t* dyn_begin, const uint32_t* dyn_end, size_t n_subframes, size_t n_dyn,
+                           std::vector<uint2>& ranges, std::string& why)
+{
+    // shared prefix = instances before the first subframe's range
+    uint32_t prefix = n_dyn ? 0xFFFFFFFFu : 0;
+    for(size_t i = 0; i < n_subframes; ++i)
+    {
+        if(dyn_begin[i] > dyn_end[i] || dyn_end[i] > n_dyn) { why = "bad range " + std::to_string(i); return false; }
+        if(dyn_begin[i] < prefix) prefix = dyn_begin[i];
+    }
+    ranges.resize(n_subframes);
+    for(size_t i = 0; i < n_subframes; ++i)
+    {
+        const uint32_t a = dyn_begin[i], b = dyn_end[i];
+        if(a >= (1u << 20) || prefix + (b - a) > (uint32_t)PTGPU_MAX_DYNAMIC_PER_SUBFRAME)
+        {
+            why = "subframe " + std::to_string(i) + " sees " + std::to_string(prefix + (b - a)) + " dynamic instances (limit " +
+                std::to_string(PTGPU_MAX_DYNAMIC_PER_SUBFRAME) + ")";
+            return false;
+        }
+        ranges[i] = make_uint2(prefix, a | ((b - a) << 20));
+    }
+    return true;
+}
+
 int upload_frame_common(ptgpu_ctx* ctx, const ptgpu_subframe* subframes, size_t n_subframes,
                         const ptgpu_tlas_instance* dyn, size_t n_dyn, const std::vector<uint2>& ranges)
 {
@@ -459,7 +529,7 @@ int upload_frame_common(ptgpu_ctx* ctx, const ptgpu_subframe* subframes, size_t 
         off += sz_dyn;
         WideInstance* wi = (WideInstance*)(st + ((off + 15) & ~size_t(15)));
         for(size_t i = 0; i < n_dyn; ++i)
-            if(!make_wide_instance(ctx->wide_host, dyn[i], (uint32_t)(ctx->n_static + i), wi[i]))
+            if(!make_wide_instance(ctx->host->wide, dyn[i], (uint32_t)(ctx->n_static + i), wi[i]))
                 return fail(ctx, "dynamic instance %zu references an unknown BLAS (node_offset %u)", i, dyn[i].blas.node_offset);
         CK(cudaMemcpyAsync(ctx->winst.p + ctx->n_static, wi, sz_win, cudaMemcpyHostToDevice, ctx->stream));
         off = ((off + 15) & ~size_t(15)) + sz_win;
@@ -526,6 +596,14 @@ int ptgpu_create(ptgpu_ctx** out, int device, const ptgpu_config* cfg)
     return 0;
 }
 
+int ptgpu_warm_up(int device)
+{
+    // creates the device's primary CUDA context (what the first CUDA call on a device pays for: ~1 s per GPU,
+    // serialised by the driver), so that a host can overlap it with its own start-up work
+    if(cudaSetDevice(device) != cudaSuccess) return 1;
+    return cudaFree(nullptr) == cudaSuccess ? 0 : 1;
+}
+
 void ptgpu_destroy(ptgpu_ctx* ctx)
 {
     if(!ctx) return;
@@ -587,11 +665,12 @@ static int upload_static_common(
     ctx->n_static_nodes = n_nodes; ctx->n_static = n_static; ctx->n_verts = n_verts; ctx->n_indices = n_indices;
     ctx->host_static.assign(instances, instances + n_static);
 
-    // GPU traversal layout: a wide BVH per distinct BLAS + one static TLAS
+    // GPU traversal layout: a compressed BVH per distinct BLAS + one static TLAS (+ the flat static scene)
     std::string err;
-    if(!build_wide_scene(nodes, n_nodes, links, indices, n_indices, pos, n_verts, instances, n_static, ctx->wide_host, err, meshes, n_meshes))
-        return fail(ctx, "wide BVH build failed: %s", err.c_str());
-    const WideScene& w = ctx->wide_host;
+    ctx->host = get_host_scene(nodes, n_nodes, links, n_links, indices, n_indices, pos, n_verts, instances, n_static,
+                               meshes, n_meshes, ctx->flat != 0, err);
+    if(!ctx->host) return fail(ctx, "%s", err.c_str());
+    const WideScene& w = ctx->host->wide;
     {   // shading records: the nine attribute vectors of every triangle, contiguous (pt_scene.cuh)
         std::vector<float4> rec(9 * (n_indices / 3), make_float4(0.f, 0.f, 0.f, 0.f));
         for(const WideBlasInfo& bi : w.blas_info)
@@ -625,32 +704,11 @@ static int upload_static_common(
     CK(cudaMemcpy(ctx->wtlas.p, w.tlas.data(), w.tlas.size() * sizeof(WideNode), cudaMemcpyHostToDevice));
     ctx->n_wtlas = w.tlas.size();
     // flat static scene: appended to the compressed node / triangle arrays (its indices are absolute)
-    std::shared_ptr<const FlatScene> flat;
-    ctx->have_flat = false; ctx->flat_root = 0xFFFFFFFFu;
-    if(ctx->flat)
+    const FlatScene* flat = ctx->host->have_flat ? &ctx->host->flat : nullptr;
+    ctx->have_flat = flat != nullptr; ctx->flat_root = 0xFFFFFFFFu;
+    if(flat)
     {
-        const uint32_t node_base = (uint32_t)(w.cw_nodes.size() / 5), tri_base = (uint32_t)(w.cw_tris.size() / 3);
-        uint64_t h = 0xCBF29CE484222325ull;
-        h = hash_bytes(h, instances, n_static * sizeof(ptgpu_tlas_instance));
-        h = hash_bytes(h, indices, n_indices * 4);
-        h = hash_bytes(h, pos, n_verts * sizeof(ptgpu_float3));
-        h = hash_bytes(h, &node_base, 4); h = hash_bytes(h, &tri_base, 4);
-        std::lock_guard<std::mutex> lock(g_flat_mutex);   // a second context waits for the first one's build
-        auto it = g_flat_cache.find(h);
-        if(it != g_flat_cache.end()) flat = it->second;
-        else
-        {
-            auto fs = std::make_shared<FlatScene>();
-            if(!build_flat_scene(w, indices, pos, instances, n_static, node_base, tri_base, *fs, err))
-                return fail(ctx, "flat scene build failed: %s", err.c_str());
-            if(2 * fs->depth + 8 > (uint32_t)CW_STACK)
-                return fail(ctx, "flat scene: BVH depth %u needs a deeper traversal stack than CW_STACK", fs->depth);
-            if(g_flat_cache.size() >= 2) g_flat_cache.erase(g_flat_cache.begin());
-            g_flat_cache[h] = fs;
-            flat = fs;
-        }
-        ctx->have_flat = true;
-        ctx->flat_root = node_base; ctx->flat_top = flat->n_top; ctx->flat_depth = flat->depth;
+        ctx->flat_root = (uint32_t)(w.cw_nodes.size() / 5); ctx->flat_top = flat->n_top; ctx->flat_depth = flat->depth;
         ctx->flat_tris = flat->n_tris; ctx->flat_nodes = flat->nodes.size() / 5;
         ctx->flat_build_seconds = flat->build_seconds;
     }
@@ -804,21 +862,10 @@ int ptgpu_set_frame_ranges(
     if(!ctx->have_static) return fail(ctx, "ptgpu_set_frame_ranges before ptgpu_upload_static");
     if(!subframes || n_subframes == 0 || !dyn_begin || !dyn_end) return fail(ctx, "ptgpu_set_frame_ranges: null argument");
     if(use(ctx)) return 1;
-    // shared prefix = instances before the first subframe's range (frame-static extras)
-    uint32_t prefix = n_dyn ? 0xFFFFFFFFu : 0;
-    for(size_t i = 0; i < n_subframes; ++i)
-    {
-        if(dyn_begin[i] > dyn_end[i] || dyn_end[i] > n_dyn) return fail(ctx, "ptgpu_set_frame_ranges: bad range %zu", i);
-        if(dyn_begin[i] < prefix) prefix = dyn_begin[i];
-    }
-    std::vector<uint2> ranges(n_subframes);
-    for(size_t i = 0; i < n_subframes; ++i)
-    {
-        uint32_t a = dyn_begin[i], b = dyn_end[i];
-        if(a >= (1u << 20) || prefix + (b - a) > (uint32_t)PTGPU_MAX_DYNAMIC_PER_SUBFRAME)
-            return fail(ctx, "ptgpu_set_frame_ranges: subframe %zu sees %u dynamic instances (limit %d)", i, prefix + (b - a), PTGPU_MAX_DYNAMIC_PER_SUBFRAME);
-        ranges[i] = make_uint2(prefix, a | ((b - a) << 20));
-    }
+    std::vector<uint2> ranges;
+    std::string why;
+    if(!encode_dynamic_ranges(dyn_begin, dyn_end, n_subframes, n_dyn, ranges, why))
+        return fail(ctx, "ptgpu_set_frame_ranges: %s", why.c_str());
     ctx->frame_has_ref_tlas = false;
     return upload_frame_common(ctx, subframes, n_subframes, dyn_instances, n_dyn, ranges);
 }
@@ -1136,7 +1183,8 @@ int ptgpu_read_counters(ptgpu_ctx* ctx, uint64_t out[PTGPU_CNT_COUNT])
 int ptgpu_scene_stats(ptgpu_ctx* ctx, uint64_t out[8])
 {
     if(!ctx || !out) return 1;
-    const WideScene& w = ctx->wide_host;
+    static const WideScene empty_scene;
+    const WideScene& w = ctx->host ? ctx->host->wide : empty_scene;
     uint64_t ref_bytes = ctx->n_static_nodes * (24 + 64) + ctx->n_indices * 4 + ctx->n_verts * 64 + ctx->n_static * 160;
     uint64_t wide_bytes = w.nodes.size() * sizeof(WideNode) + w.tris.size() * 16 + w.tlas.size() * sizeof(WideNode) +
         ctx->n_static * sizeof(WideInstance) + ctx->n_indices * 4 + ctx->n_verts * 48 + ctx->n_static * 160;
@@ -1193,6 +1241,31 @@ int ptgpu_host_flat_check(
         }
     }
     if(err && err_len) { strncpy(err, e.c_str(), err_len - 1); err[err_len - 1] = 0; }
+    return 1;
+}
+
+int ptgpu_host_prepare_static(
+    const ptgpu_bvh_node* nodes, size_t n_nodes, const ptgpu_bvh_link* links, size_t n_links,
+    const uint32_t* indices, size_t n_indices, const ptgpu_float3* pos, size_t n_verts,
+    const ptgpu_tlas_instance* instances, size_t n_static, int32_t flat, char* err, size_t err_len)
+{
+    std::string e;
+    if(err && err_len) err[0] = 0;
+    if(!nodes || !links || !indices || !pos || !instances || n_links != 8 * n_nodes || n_static == 0) e = "bad arguments";
+    else if(get_host_scene(nodes, n_nodes, links, n_links, indices, n_indices, pos, n_verts, instances, n_static, nullptr, 0, flat != 0, e)) return 0;
+    if(err && err_len) { strncpy(err, e.c_str(), err_len - 1); err[err_len - 1] = 0; }
+    return 1;
+}
+
+int ptgpu_host_check_dynamic_ranges(const uint32_t* dyn_begin, const uint32_t* dyn_end, size_t n_subframes, size_t n_dyn,
+                                    char* err, size_t err_len)
+{
+    std::vector<uint2> ranges;
+    std::string why;
+    if(err && err_len) err[0] = 0;
+    if(!dyn_begin || !dyn_end || n_subframes == 0) why = "bad arguments";
+    else if(encode_dynamic_ranges(dyn_begin, dyn_end, n_subframes, n_dyn, ranges, why)) return 0;
+    if(err && err_len) { strncpy(err, why.c_str(), err_len - 1); err[err_len - 1] = 0; }
     return 1;
 }
 

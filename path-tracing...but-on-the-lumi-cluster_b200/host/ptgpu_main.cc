@@ -102,9 +102,16 @@ int main(int argc, char** argv)
     }
 
     double t0 = now_s();
+    // Creating eight CUDA contexts takes the driver ~7 s on an 8-GPU box: start that now, one thread per GPU, and load
+    // the scene (1.4 s) and do the library's host-side BVH builds (3 s, once for all GPUs) meanwhile.
+    std::vector<std::thread> warm;
+    for(int g = 0; g < gpus; ++g) warm.emplace_back([g]() { ptgpu_warm_up(g); });
     scene loaded = load_scene();
     printf("EXECUTION TIME OF load_scene() : %.0fms\n", 1e3 * (now_s() - t0));
     if(frame_end == 0) frame_end = get_animation_frame_count(loaded); // main.cc:74 as intended
+    if(loaded.subframes.empty()) ptgpu_detail::prepare_static(loaded);
+    for(auto& w : warm) w.join();
+    printf("START-UP (contexts, scene, static BVHs) : %.0fms\n", 1e3 * (now_s() - t0));
 
     if(!dump_dir.empty())
     {   // test hook: the arrays this program hands to the C ABI (main.cc:29-37), so that another host can
@@ -178,6 +185,8 @@ int main(int argc, char** argv)
             std::vector<scene> scenes(N_SCENES, loaded);
             uint scene_frame[N_SCENES] = {};
             ptgpu_detail::renderer<scene> r(g, cfg);
+            const double t_ctx = now_s() - render_t0;
+            bool first = true;
             std::vector<std::vector<uint8_t>> images(N_IMAGES, std::vector<uint8_t>(r.bmp_size()));
             uint image_frame[N_IMAGES] = {};
             slot_queue scenes_free, scenes_ready, images_free, images_ready;
@@ -213,6 +222,11 @@ int main(int argc, char** argv)
                 if(si < 0) break;
                 int ii = images_free.pop();
                 timed(us_render, [&] { r.render_bmp(scenes[si], images[ii].data()); });
+                if(first)
+                {   // start-up cost of this worker: CUDA context, then scene upload + BVH builds inside the first frame
+                    fprintf(stderr, "GPU %d: context after %.2fs, first frame (with the scene upload) done after %.2fs\n", g, t_ctx, now_s() - render_t0);
+                    first = false;
+                }
                 image_frame[ii] = scene_frame[si];
                 scenes_free.push(si);
                 images_ready.push(ii);

@@ -151,3 +151,45 @@ def test_own_blas_builder(pkg, oracle):
         p(arrs["indices"]), arrs["indices"].shape[0], p(arrs["pos"]), arrs["pos"].shape[0],
         p(meshes[1:]), meshes.shape[0] - 1, p(arrs["instances"]), arrs["instances"].shape[0], out, err, 512)
     assert rc != 0 and b"does not match" in err.value
+
+
+def test_oversize_dynamic_sets_are_rejected(pkg):
+    """ADVICE round 1: the kernels hold a subframe's per-frame instances as one 24-bit group / 16 stack entries;
+    ptgpu_set_frame_ranges must refuse more instead of corrupting the traversal stack."""
+    lib = pkg.load_library()
+    err = C.create_string_buffer(256)
+
+    def check(begin, end, n_dyn):
+        b, e = np.asarray(begin, np.uint32), np.asarray(end, np.uint32)
+        return lib.ptgpu_host_check_dynamic_ranges(b.ctypes.data_as(C.c_void_p), e.ctypes.data_as(C.c_void_p), len(b), n_dyn, err, 256)
+
+    assert check([2, 5], [5, 7], 7) == 0                   # the animation: prefix 2 (logo, buddha) + 2-3 per subframe
+    assert check([0], [16], 16) == 0                       # exactly the limit
+    assert check([0], [17], 17) != 0 and b"17 dynamic instances" in err.value
+    assert check([10, 12], [12, 20], 20) != 0              # prefix 10 + 8 of its own = 18
+    assert check([3], [2], 4) != 0 and b"bad range" in err.value
+    assert check([0], [5], 4) != 0                         # range beyond the instance array
+
+
+def test_flat_scene_build_of_a_small_scene(pkg, oracle):
+    """The flat static scene (all static instances as world-space triangles under one 8-wide BVH) of the stress
+    scene's static part (the terrain, 73 730 triangles): every triangle a leaf exactly once, vertices inside their
+    quantised leaf boxes and every ancestor's slot box."""
+    lib = pkg.load_library()
+    v = oracle.setup_stress_scene()
+    try:
+        st = pkg.scene_io.static_from_view(v)
+        arrs = {k: np.ascontiguousarray(a) for k, a in st.items()}
+        out = (C.c_uint64 * 8)()
+        err = C.create_string_buffer(512)
+        p = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+        rc = lib.ptgpu_host_flat_check(
+            p(arrs["nodes"]), arrs["nodes"].shape[0], p(arrs["links"]), arrs["links"].shape[0],
+            p(arrs["indices"]), arrs["indices"].shape[0], p(arrs["pos"]), arrs["pos"].shape[0],
+            p(arrs["instances"]), arrs["instances"].shape[0], out, err, 512)
+    finally:
+        oracle.restore_scene()
+    assert rc == 0, err.value
+    n_tris, n_nodes, n_top, depth, bad = list(out)[:5]
+    assert n_tris == 73730 and bad == 0
+    assert 73730 / 8 < n_nodes < 73730 / 3 and 0 < depth <= 20

@@ -19,6 +19,9 @@ import pytest
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 STUDENT_ID = 152121358
+# fraction of single samples that must agree with path_trace_pixel to 1e-3 (measured 0.981-0.999: the bar allows
+# twice the measured misses; one rounding difference can flip a lobe choice and change a whole path)
+BAR_SAMPLES = 0.96
 
 
 def mae255(a_bgra, b_bgra):
@@ -123,7 +126,8 @@ def test_path_trace_pixel_samples(frames, oracle, frame):
     ref = np.stack([oracle.trace_sample(int(a), int(b), int(c)) for (a, b), c in zip(xy, si)])
     got = r.trace_samples(xy, si)
     rel = np.abs(got - ref).max(1) / np.maximum(np.abs(ref).max(1), 1e-4)
-    assert (rel < 1e-3).mean() > 0.90, (rel < 1e-3).mean()
+    print("frame %d: %.4f of %d samples within 1e-3 of path_trace_pixel" % (frame, (rel < 1e-3).mean(), n))
+    assert (rel < 1e-3).mean() > BAR_SAMPLES, (rel < 1e-3).mean()
     assert np.isfinite(got).all()
     # the three kernels run the same device functions; nvcc contracts FMAs per kernel, so they agree
     # to rounding (and exactly on most pixels), not bit for bit
@@ -192,7 +196,7 @@ def test_golden_frame_0(frames, oracle):
     mse = ((rgb.astype(np.float64) - gold.astype(np.float64)) ** 2).mean()
     psnr = 10 * np.log10(255.0 ** 2 / mse)
     print("golden frame 0: MAE %.4f/255, PSNR %.1f dB" % (mae, psnr))
-    assert mae <= 0.25 and psnr >= 40.0
+    assert mae <= 0.06 and psnr >= 55.0          # measured 0.026 and 62.6 dB
     assert (bgra[..., 3] == 255).all()
     # fused BMP packing = write_bmp of the BGRA frame (bmp.cc:15-52), byte for byte
     bmp = r.render_bmp()
@@ -413,6 +417,22 @@ def test_full_size_properties(frames, oracle):
     for y in (40, 180, 300):
         o_rgb, o_bgra = oracle.render_rect(0, y, 640, 1, 0, 256, 1)
         assert mae255(a[y:y + 1], o_bgra) <= 1.0
+
+
+@pytest.mark.parametrize("frame", [520, 1400])
+def test_every_10th_row_at_full_spp(frames, oracle, frame):
+    """Content frames at the full 256 spp on every 10th row (36 rows, 5.9 M paths): the image-mean bar of
+    BASELINE.json (1e-3 relative) and the tonemapped MAE, asserted at the sample count the metric is quoted on."""
+    r = frames.use(frame)
+    rows = list(range(0, 360, 10))
+    g_rgb = np.concatenate([r.render_rect(0, y, 640, 1, 0, 256, 1)[0] for y in rows])
+    g_bgra = np.concatenate([r.render_rect(0, y, 640, 1, 0, 256, 1)[1] for y in rows])
+    o = [oracle.render_rect(0, y, 640, 1, 0, 256, 1) for y in rows]
+    o_rgb, o_bgra = np.concatenate([x[0] for x in o]), np.concatenate([x[1] for x in o])
+    rel, mae = mean_rel(g_rgb, o_rgb), mae255(g_bgra, o_bgra)
+    print("frame %d, every 10th row at 256 spp: image-mean rel %.2e, MAE %.4f/255" % (frame, rel, mae))
+    assert rel <= 1e-3, rel          # measured 1.5e-5 and 8e-5
+    assert mae <= 0.25, mae          # measured 0.09 and 0.11
 
 
 def test_device_validator_matches_the_restated_validator(frames):

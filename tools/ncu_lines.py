@@ -1,6 +1,7 @@
 #!/usr/bin/env python3
 """Per-source-line aggregation of an ncu SASS source page, using nvdisasm -g line info.
-usage: ncu_lines.py <report.ncu-rep> <libptgpu.so> <kernel-substring> [top N]"""
+usage: ncu_lines.py <report.ncu-rep> <libptgpu.so> <kernel-substring> [top N] [mangled-symbol-substring]
+(the last argument picks one template instantiation in the disassembly, e.g. wf_trace_cw_kernelILb0)"""
 import collections
 import csv
 import os
@@ -41,7 +42,7 @@ def sass_lines(so, kernel):
 def main():
     rep, so, kernel = sys.argv[1], os.path.abspath(sys.argv[2]), sys.argv[3]
     top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
-    sass = sass_lines(so, kernel)
+    sass = sass_lines(so, sys.argv[5] if len(sys.argv) > 5 else kernel)
     raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
     # the page holds one table per profiled launch; take the first launch of the wanted kernel
     rows = list(csv.reader(raw.splitlines()))
