@@ -425,7 +425,7 @@ void build_mesh_tree(const uint32_t* indices, const ptgpu_float3* pos, const ptg
 //   n3  qlo.z[0..7] | qhi.x[0..7]
 //   n4  qhi.y[0..7] | qhi.z[0..7]
 // meta[slot]: inner child 0b001_11sss (24 + slot); leaf 0b{unary count}_{offset from tri_base}; 0 = empty —
-// or, with CW_PAD_EMPTY (pt_scene.cuh), an empty slot holds an inverted box and a copy of a real child's meta.
+// an empty slot holds an inverted box (never hit) and a copy of a real child's meta (pt_scene.cuh).
 // Children sit in the slot whose octant direction best matches their offset from the node centre, so
 // a ray visits slots in the order (slot XOR ray octant), high to low, without sorting distances.
 
@@ -760,9 +760,8 @@ struct CwEmitter
                 meta[s] = (uint8_t)((((1u << cnt) - 1u) << 5) | off);
             }
         }
-#if CW_PAD_EMPTY
         {   // empty slots: inverted box + the meta byte of a real child (pt_scene.cuh)
-            static_assert(CW_LEAF_MAX == 1, "CW_PAD_EMPTY needs one triangle per leaf child");
+            static_assert(CW_LEAF_MAX == 1, "the maskless box test needs one triangle per leaf child");
             int first_used = -1;
             for(int s = 0; s < CW_WIDTH && first_used < 0; ++s) if(child_in_slot[s] >= 0) first_used = s;
             if(first_used < 0) { err = "node without children"; return 0; }
@@ -773,7 +772,6 @@ struct CwEmitter
                 meta[s] = meta[first_used];
             }
         }
-#endif
         // pass 2: inner children, stored contiguously from child_base in slot order
         uint32_t deepest = 0, inner_rank = 0;
         for(int s = 0; s < CW_WIDTH; ++s)
@@ -1482,7 +1480,7 @@ uint64_t verify_wide_scene(const WideScene& ws, size_t n_static, std::string& er
             {
                 const uint32_t meta = (metaw[s >> 2] >> (8 * (s & 3))) & 0xFF;
                 if(meta == 0) { if(imask & (1u << s)) fail("imask set on an empty slot"); continue; }
-                bool padding = false;   // CW_PAD_EMPTY: an empty slot is an inverted box
+                bool padding = false;   // an empty slot is an inverted box
                 for(int a = 0; a < 3; ++a)
                     if(((q[a][s >> 2] >> (8 * (s & 3))) & 0xFF) > ((q[3 + a][s >> 2] >> (8 * (s & 3))) & 0xFF)) padding = true;
                 if(padding) { if(imask & (1u << s)) fail("imask set on a padding slot"); continue; }

@@ -18,6 +18,9 @@
 namespace pt {
 
 #define CW_MARK_X 0xFFFFFFFFu
+#ifndef CW_DYN_UNION
+#define CW_DYN_UNION 1
+#endif
 
 // Traversal stack storage. LocalStack: a per-thread array (local memory). HybridStack: the first
 // CW_SM_STACK entries in shared memory laid out [entry][thread] (bank = thread, conflict-free for any
@@ -42,23 +45,48 @@ struct HybridStack
     PT_D uint2 get(int i) const { return i < CW_SM_STACK ? sm[i * stride] : lo[i - CW_SM_STACK]; }
 };
 
+// Per-query traversal state. Kept as small as the algorithm allows: wf_trace_cw_kernel runs at 64 registers
+// (8 blocks per SM), and every value held here across the box test is one the test cannot use. So the state
+// does NOT hold the world-space ray (o and idir are the world ray while outside an instance; on the rare exit
+// from one — <= 7 per-frame instances — the ray is read again from where the caller keeps it, see the `World`
+// argument of the functions below), nor the sign bits (they follow from the octant), nor the subframe, nor a
+// hit distance of its own: with a hit recorded (inst != CW_NO_HIT) the hit distance IS tmax.
 struct CwState
 {
-    v3 ro, rd;          // world-space ray
     v3 o, idir;         // current space (world or instance): origin and clamped 1/direction
-    v3 S;               // triangle-test preprocess of the instance-space direction (math.hh:340-356)
+    v3 S;               // triangle-test preprocess of the current-space direction (math.hh:340-356)
     int axis;
-    uint32_t oct_inv4;  // ray octant, replicated in 4 bytes
-    uint32_t sign_bits; // bit0: d.x < 0, bit1: d.y < 0, bit2: d.z < 0 (current space)
+    uint32_t oct_inv4;  // ray octant (bit 2: d.x >= 0, bit 1: d.y >= 0, bit 0: d.z >= 0), replicated in 4 bytes
     float tmin, tmax;
     uint2 ngroup, tgroup;
     int sp;
     bool in_blas, any;
-    uint32_t cur_inst, subframe;
-    Hit hit;
+    uint32_t cur_inst;
+    float u, v;         // closest hit so far: barycentrics, (instance, primitive), facing; its distance is tmax
+    uint32_t inst, prim;
+    bool back_face;
 #ifdef WF_STATS
     uint32_t n_nodes = 0, n_tris = 0;   // census builds: node tests and triangle tests of this query
 #endif
+    PT_D bool has_hit() const { return inst != 0xFFFFFFFFu; }
+    PT_D Hit result() const
+    {
+        Hit h;
+        h.t = has_hit() ? tmax : -1.0f; h.u = u; h.v = v; h.inst = inst; h.prim = prim; h.back_face = back_face;
+        return h;
+    }
+};
+#define CW_NO_HIT 0xFFFFFFFFu
+
+// Where the world-space ray of a query lives while the state does not hold it. The plain traversal keeps it in
+// registers (it has no register budget to meet); wf_trace_cw_kernel reads it back from the path-state pool.
+struct WorldRayRegs
+{
+    v3 o, d;
+    uint32_t sub;
+    PT_D v3 origin() const { return o; }
+    PT_D v3 dir() const { return d; }
+    PT_D uint32_t subframe() const { return sub; }
 };
 
 PT_D uint32_t sign_extend_s8x4(uint32_t x)
@@ -87,7 +115,6 @@ PT_D void cw_set_space(CwState& st, v3 o, v3 d)
     st.idir = mk3(rcp_approx(fabsf(d.x) > eps ? d.x : copysignf(eps, d.x)),
                   rcp_approx(fabsf(d.y) > eps ? d.y : copysignf(eps, d.y)),
                   rcp_approx(fabsf(d.z) > eps ? d.z : copysignf(eps, d.z)));
-    st.sign_bits = (d.x < 0.0f ? 1u : 0u) | (d.y < 0.0f ? 2u : 0u) | (d.z < 0.0f ? 4u : 0u);
     // slot bit 4 = +x side, 2 = +y, 1 = +z; a ray going +x meets the -x children first
     const uint32_t oct = (d.x < 0.0f ? 0u : 4u) | (d.y < 0.0f ? 0u : 2u) | (d.z < 0.0f ? 0u : 1u);
     st.oct_inv4 = oct * 0x01010101u;
@@ -133,7 +160,7 @@ PT_D void cw_intersect_node(const float4* __restrict__ nodes, uint32_t node_inde
     const float sz = __uint_as_float((uint32_t)(((int)(ew << 8) >> 24) + 127) << 23);
     const float ax = sx * st.idir.x, ay = sy * st.idir.y, az = sz * st.idir.z;
     const float ox = (n0.x - st.o.x) * st.idir.x, oy = (n0.y - st.o.y) * st.idir.y, oz = (n0.z - st.o.z) * st.idir.z;
-    const bool nx = st.sign_bits & 1u, ny = st.sign_bits & 2u, nz = st.sign_bits & 4u;
+    const bool nx = !(st.oct_inv4 & 4u), ny = !(st.oct_inv4 & 2u), nz = !(st.oct_inv4 & 1u);
     // Boxes are culled against a slightly longer ray than the triangles: the box arithmetic rounds, so
     // with the exact tmax a node holding a hit a few ulp closer than the current one could be skipped or
     // not depending on the order in which the two were found (coincident leaf cards in the tree
@@ -175,9 +202,9 @@ PT_D void cw_intersect_node(const float4* __restrict__ nodes, uint32_t node_inde
 #define CW_FLAT_INST 0xFFFFFFFEu
 
 // The world-space ray enters the flat static scene: its leaves are triangles (in_blas), stored in world space
-PT_D void cw_enter_flat(CwState& st)
+PT_D void cw_enter_flat(CwState& st, v3 world_dir)
 {
-    tri_preprocess(st.rd, st.axis, st.S);
+    tri_preprocess(world_dir, st.axis, st.S);
     st.in_blas = true;
     st.cur_inst = CW_FLAT_INST;
 }
@@ -192,13 +219,17 @@ template<bool PARKED, class Stack>
 PT_D void cw_begin(const Scene& sc, CwState& st, Stack& stack, uint32_t subframe, v3 ro, v3 rd,
                    float tmin, float tmax, bool any)
 {
-    st.ro = ro; st.rd = rd; st.tmin = tmin; st.tmax = tmax; st.any = any; st.subframe = subframe;
-    st.hit.t = -1.0f; st.hit.u = 0.0f; st.hit.v = 0.0f; st.hit.inst = 0xFFFFFFFFu; st.hit.prim = 0; st.hit.back_face = false;
+    st.tmin = tmin; st.tmax = tmax; st.any = any;
+    st.u = 0.0f; st.v = 0.0f; st.inst = CW_NO_HIT; st.prim = 0; st.back_face = false;
     st.sp = 0; st.in_blas = false; st.cur_inst = 0; st.axis = 2; st.S = mk3(0, 0, 1);
     cw_set_space(st, ro, rd);
     const uint2 r = __ldg(sc.dyn_range + subframe);
     const uint32_t p = r.x, a = r.y & 0xFFFFFu, len = r.y >> 20;
     uint32_t mask = 0;
+#if CW_DYN_UNION
+    // one box around the whole set first: most bounce and shadow rays miss it and skip the loop
+    if(p + len > 0u && box_hit(__ldg(sc.dyn_union + 2 * subframe), __ldg(sc.dyn_union + 2 * subframe + 1), ro, st.idir, tmin, tmax))
+#endif
     for(uint32_t k = 0; k < p + len; ++k)
     {
         const uint32_t id = sc.n_static + (k < p ? k : a + (k - p));
@@ -226,19 +257,20 @@ PT_D void cw_begin(const Scene& sc, CwState& st, Stack& stack, uint32_t subframe
         if(PARKED)
         {
             stack.set(st.sp++, make_uint2(__float_as_uint(st.idir.x), __float_as_uint(st.idir.y)));
-            stack.set(st.sp++, make_uint2(__float_as_uint(st.idir.z), (st.oct_inv4 & 0xFFu) | (st.sign_bits << 8)));
+            stack.set(st.sp++, make_uint2(__float_as_uint(st.idir.z), st.oct_inv4 & 0xFFu));
         }
         stack.set(st.sp++, make_uint2(CW_MARK_X, 0u));
     }
-    cw_enter_flat(st);
+    cw_enter_flat(st, rd);
     st.ngroup = make_uint2(sc.flat_root, 0x80000000u);
 }
 
-PT_D uint32_t cw_decode_instance(const Scene& sc, const CwState& st, uint32_t base, uint32_t bit)
+template<class World>
+PT_D uint32_t cw_decode_instance(const Scene& sc, const World& world, uint32_t base, uint32_t bit)
 {
     if(base & 0x80000000u)
     {   // dynamic instance k of the subframe
-        const uint2 r = __ldg(sc.dyn_range + st.subframe);
+        const uint2 r = __ldg(sc.dyn_range + world.subframe());
         const uint32_t p = r.x, a = r.y & 0xFFFFFu, k = (base & 0x7FFFFFFFu) + bit;
         return sc.n_static + (k < p ? k : a + (k - p));
     }
@@ -246,19 +278,20 @@ PT_D uint32_t cw_decode_instance(const Scene& sc, const CwState& st, uint32_t ba
 }
 
 // ray_query_enter_blas (ray_query.hh:153-182) on the compressed layout
-template<class Stack>
-PT_D void cw_enter_instance(const Scene& sc, CwState& st, Stack& stack, uint32_t id)
+template<class Stack, class World>
+PT_D void cw_enter_instance(const Scene& sc, CwState& st, Stack& stack, const World& world, uint32_t id)
 {
     st.cur_inst = id;
     const WideInstance* wi = sc.winst + id;
     const float4 r0 = __ldg(&wi->inv0), r1 = __ldg(&wi->inv1), r2 = __ldg(&wi->inv2);
     const uint32_t root = __ldg(&wi->cw_root);
-    const v3 o = mk3(r0.x * st.ro.x + r0.y * st.ro.y + r0.z * st.ro.z + r0.w,
-                     r1.x * st.ro.x + r1.y * st.ro.y + r1.z * st.ro.z + r1.w,
-                     r2.x * st.ro.x + r2.y * st.ro.y + r2.z * st.ro.z + r2.w);
-    const v3 d = mk3(r0.x * st.rd.x + r0.y * st.rd.y + r0.z * st.rd.z,
-                     r1.x * st.rd.x + r1.y * st.rd.y + r1.z * st.rd.z,
-                     r2.x * st.rd.x + r2.y * st.rd.y + r2.z * st.rd.z);
+    const v3 ro = world.origin(), rd = world.dir();
+    const v3 o = mk3(r0.x * ro.x + r0.y * ro.y + r0.z * ro.z + r0.w,
+                     r1.x * ro.x + r1.y * ro.y + r1.z * ro.z + r1.w,
+                     r2.x * ro.x + r2.y * ro.y + r2.z * ro.z + r2.w);
+    const v3 d = mk3(r0.x * rd.x + r0.y * rd.y + r0.z * rd.z,
+                     r1.x * rd.x + r1.y * rd.y + r1.z * rd.z,
+                     r2.x * rd.x + r2.y * rd.y + r2.z * rd.z);
     cw_set_space(st, o, d);
     tri_preprocess(d, st.axis, st.S);
     st.in_blas = true;
@@ -287,11 +320,11 @@ PT_D void cw_test_triangle(const Scene& sc, CwState& st, uint32_t tri)
     const uint32_t bw = __float_as_uint(b.w);
     const uint32_t inst = st.cur_inst == CW_FLAT_INST ? (bw & 0x7FFFFFFFu) : st.cur_inst;
     const bool closer = t < st.tmax;
-    const bool tie = st.hit.t >= 0.0f && t == st.hit.t &&
-        (inst < st.hit.inst || (inst == st.hit.inst && prim < st.hit.prim));
+    const bool tie = st.has_hit() && t == st.tmax &&
+        (inst < st.inst || (inst == st.inst && prim < st.prim));
     if(ok && t > st.tmin && (closer || tie))
     {
-        st.hit.t = t; st.hit.u = u; st.hit.v = v; st.hit.inst = inst; st.hit.prim = prim; st.hit.back_face = bf != ((bw >> 31) != 0u);
+        st.u = u; st.v = v; st.inst = inst; st.prim = prim; st.back_face = bf != ((bw >> 31) != 0u);
         st.tmax = t;
         if(st.any) { st.sp = 0; st.ngroup.y = 0u; st.tgroup.y = 0u; }
     }
@@ -323,19 +356,19 @@ PT_D void cw_node_phase(const Scene& sc, CwState& st, Stack& stack, const TopLev
 }
 
 // instance phase (TLAS context): enter one instance of the leaf group, park everything else
-template<class Stack>
-PT_D void cw_instance_phase(const Scene& sc, CwState& st, Stack& stack)
+template<class Stack, class World>
+PT_D void cw_instance_phase(const Scene& sc, CwState& st, Stack& stack, const World& world)
 {
     const uint32_t bit = 31u - (uint32_t)__clz(st.tgroup.y);
     st.tgroup.y &= ~(1u << bit);
     if(st.ngroup.y > 0x00FFFFFFu) stack.set(st.sp++, st.ngroup);
     if(st.tgroup.y) stack.set(st.sp++, st.tgroup);
-    cw_enter_instance(sc, st, stack, cw_decode_instance(sc, st, st.tgroup.x, bit));
+    cw_enter_instance(sc, st, stack, world, cw_decode_instance(sc, world, st.tgroup.x, bit));
 }
 
 // pop phase; returns false when the query is complete
-template<class Stack>
-PT_D bool cw_pop_phase(const Scene& sc, CwState& st, Stack& stack)
+template<class Stack, class World>
+PT_D bool cw_pop_phase(const Scene& sc, CwState& st, Stack& stack, const World& world)
 {
     if(st.ngroup.y <= 0x00FFFFFFu)
     {
@@ -344,14 +377,14 @@ PT_D bool cw_pop_phase(const Scene& sc, CwState& st, Stack& stack)
         if(e.y == 0u)
         {   // exit marker: BLAS finished, back to world space
             st.in_blas = false;
-            cw_set_space(st, st.ro, st.rd);
+            cw_set_space(st, world.origin(), world.dir());
             st.ngroup = make_uint2(0u, 0u);
         }
         else
         {
             st.ngroup = e;
             // a node group met in world space with a flat static scene is that scene's root (dyn_first)
-            if(!st.in_blas && e.y > 0x00FFFFFFu && sc.flat_root != 0xFFFFFFFFu) cw_enter_flat(st);
+            if(!st.in_blas && e.y > 0x00FFFFFFu && sc.flat_root != 0xFFFFFFFFu) cw_enter_flat(st, world.dir());
         }
     }
     return true;
@@ -364,6 +397,7 @@ PT_D bool trace_cw(const Scene& sc, uint32_t subframe, v3 origin, v3 dir, float 
     uint2 stack_mem[CW_STACK];
     LocalStack stack{stack_mem};
     CwState st;
+    const WorldRayRegs world{origin, dir, subframe};
     cw_begin<false>(sc, st, stack, subframe, origin, dir, tmin, tmax, ANY);
     for(;;)
     {
@@ -378,10 +412,10 @@ PT_D bool trace_cw(const Scene& sc, uint32_t subframe, v3 origin, v3 dir, float 
                 cw_test_triangle(sc, st, st.tgroup.x + bit);
             }
         }
-        else if(st.tgroup.y) cw_instance_phase(sc, st, stack);
-        if(!cw_pop_phase(sc, st, stack)) break;
+        else if(st.tgroup.y) cw_instance_phase(sc, st, stack, world);
+        if(!cw_pop_phase(sc, st, stack, world)) break;
     }
-    hit = st.hit;
+    hit = st.result();
 #ifdef WF_STATS
     if(census) { census[0] = st.n_nodes; census[1] = st.n_tris; }
 #endif

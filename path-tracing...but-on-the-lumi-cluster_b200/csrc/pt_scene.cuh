@@ -98,6 +98,7 @@ struct Scene
     const WideInstance* winst;      // parallel to `instances`
     const WideNode* wtlas;          // static TLAS over static instances (leaf slot = instance index)
     const uint2* dyn_range;         // per subframe: dynamic instance set {prefix p, a | len << 20} (ptgpu_api.cu)
+    const float4* dyn_union;        // per subframe: lo, hi of the world box around that set
     // compressed 8-wide layout (bvh_wide.cu: build_cw_*, pt_cwbvh.cuh)
     const float4* cwnodes;          // 5 float4 (80 B) per node, all BLASes then the static TLAS
     const float4* cwtris;           // 3 float4 per triangle, leaf order; p0.w = primitive id (bits)

@@ -326,6 +326,25 @@ constexpr int CW_PEND = CW_PEND_N;
 #ifndef WF_CW_BLOCKS
 #define WF_CW_BLOCKS 8
 #endif
+
+// The world-space ray of the lane's query, read back from the path-state pool on the rare occasions the
+// traversal needs it again (entering or leaving one of the <= 7 per-frame instances: ~5 M times per frame
+// against 220 M queries): six registers and the subframe index the traversal state does not hold (pt_cwbvh.cuh).
+struct SlotRay
+{
+    const Scene& sc;
+    const RenderJob& job;
+    const WaveBuffers& wb;
+    const uint32_t& slot;
+    const bool& shadow;
+    PT_D v3 origin() const { const float4 f = wb.ray_o[slot]; return mk3(f.x, f.y, f.z); }
+    PT_D v3 dir() const { const float4 f = shadow ? wb.shadow_d[slot] : wb.ray_d[slot]; return mk3(f.x, f.y, f.z); }
+    PT_D uint32_t subframe() const
+    {
+        const int sample = job.s_begin + wb.cursor[slot].x * job.s_stride;
+        return sample < 0 ? 0u : (uint32_t)sample / (uint32_t)sc.samples_per_subframe;
+    }
+};
 template<bool TOP>
 __global__ void __launch_bounds__(WF_TRACE_THREADS, WF_CW_BLOCKS)
 wf_trace_cw_kernel(Scene sc, RenderJob job, WaveBuffers wb)
@@ -340,8 +359,6 @@ wf_trace_cw_kernel(Scene sc, RenderJob job, WaveBuffers wb)
         __syncthreads();
     }
     const unsigned lane = threadIdx.x & 31u;
-    const uint32_t n_s0 = wb.cnt->n_seg[0], n_s1 = wb.cnt->n_seg[1], n_s2 = wb.cnt->n_seg[2];
-    const uint32_t n_entries = n_s0 + n_s1 + n_s2;
     uint32_t res_base = 0, res_n = 0;
     bool exhausted = false;
 
@@ -355,6 +372,7 @@ wf_trace_cw_kernel(Scene sc, RenderJob job, WaveBuffers wb)
     int np = 0;
     CwState st;
     st.ngroup = make_uint2(0u, 0u); st.tgroup = make_uint2(0u, 0u); st.sp = 0; st.in_blas = false; st.any = false;
+    const SlotRay world{sc, job, wb, slot, st.any};
 
     for(;;)
     {
@@ -362,6 +380,9 @@ wf_trace_cw_kernel(Scene sc, RenderJob job, WaveBuffers wb)
         if(32 - __popc(act) >= job.min_active || act == 0u)
         {
             // -- refill idle lanes from the ray queue ------------------------------------------------
+            // (the segment extents are read here, not held in registers across the traversal)
+            const uint32_t n_s0 = wb.cnt->n_seg[0], n_s1 = wb.cnt->n_seg[1], n_s2 = wb.cnt->n_seg[2];
+            const uint32_t n_entries = n_s0 + n_s1 + n_s2;
             const unsigned idle = ~act;
             const uint32_t want = (uint32_t)__popc(idle);
             const uint32_t my_rank = (uint32_t)__popc(idle & ((1u << lane) - 1u));
@@ -421,12 +442,13 @@ wf_trace_cw_kernel(Scene sc, RenderJob job, WaveBuffers wb)
                     if(np == 0)
                     {   // query complete: write the result
                         active = false;
-                        if(st.any) wb.visible[slot] = st.hit.t < 0.0f ? 1u : 0u;
+                        if(st.any) wb.visible[slot] = st.has_hit() ? 0u : 1u;
                         else
                         {
-                            wb.hit[slot] = make_float4(st.hit.t, st.hit.u, st.hit.v, __uint_as_float(st.hit.inst));
-                            wb.hit_prim[slot] = st.hit.prim | (st.hit.back_face ? 0x80000000u : 0u);
-                            wb.status[slot] = (st.hit.t > 0.0f && st.hit.t < 1e3f) ? WF_ST_NEAR : WF_ST_FAR;
+                            const float t = st.has_hit() ? st.tmax : -1.0f;
+                            wb.hit[slot] = make_float4(t, st.u, st.v, __uint_as_float(st.inst));
+                            wb.hit_prim[slot] = st.prim | (st.back_face ? 0x80000000u : 0u);
+                            wb.status[slot] = (t > 0.0f && t < 1e3f) ? WF_ST_NEAR : WF_ST_FAR;
                         }
                     }
                 }
@@ -439,10 +461,9 @@ wf_trace_cw_kernel(Scene sc, RenderJob job, WaveBuffers wb)
                         {
                             st.sp -= 3;
                             const uint2 a = stack.get(st.sp), b = stack.get(st.sp + 1);
-                            st.o = st.ro;
+                            st.o = world.origin();
                             st.idir = mk3(__uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(b.x));
                             st.oct_inv4 = (b.y & 0xFFu) * 0x01010101u;
-                            st.sign_bits = (b.y >> 8) & 7u;
                             st.in_blas = false;
                         }
                     }
@@ -453,7 +474,7 @@ wf_trace_cw_kernel(Scene sc, RenderJob job, WaveBuffers wb)
                         {
                             st.ngroup = e;
                             // a node group met in world space with a flat static scene is that scene's root (dyn_first)
-                            if(!st.in_blas && sc.flat_root != 0xFFFFFFFFu) cw_enter_flat(st);
+                            if(!st.in_blas && sc.flat_root != 0xFFFFFFFFu) cw_enter_flat(st, world.dir());
                         }
                         else st.tgroup = e;
                     }
@@ -486,7 +507,7 @@ wf_trace_cw_kernel(Scene sc, RenderJob job, WaveBuffers wb)
             g.y &= ~(1u << bit);
             if(g.y) pend[(np - 1) * WF_TRACE_THREADS] = g; else np--;
             cw_test_triangle(sc, st, g.x + bit);
-            if(st.any && st.hit.t >= 0.0f) np = 0; // any hit ends a shadow query (sp and groups are cleared)
+            if(st.any && st.has_hit()) np = 0; // any hit ends a shadow query (sp and groups are cleared)
         };
         auto enter_step = [&]() {
             // enter one instance of the group; the rest of the group and the world-space ray constants are
@@ -495,12 +516,12 @@ wf_trace_cw_kernel(Scene sc, RenderJob job, WaveBuffers wb)
             st.tgroup.y &= ~(1u << bit);
             if(st.tgroup.y) stack.set(st.sp++, st.tgroup);
             stack.set(st.sp++, make_uint2(__float_as_uint(st.idir.x), __float_as_uint(st.idir.y)));
-            stack.set(st.sp++, make_uint2(__float_as_uint(st.idir.z), (st.oct_inv4 & 0xFFu) | (st.sign_bits << 8)));
-            const uint32_t inst_id = cw_decode_instance(sc, st, st.tgroup.x, bit);
+            stack.set(st.sp++, make_uint2(__float_as_uint(st.idir.z), st.oct_inv4 & 0xFFu));
+            const uint32_t inst_id = cw_decode_instance(sc, world, st.tgroup.x, bit);
 #ifdef WF_STATS
             atomicAdd(&wb.stats[24 + min(sc.winst[inst_id].blas, 15u)], 1ull);
 #endif
-            cw_enter_instance(sc, st, stack, inst_id);
+            cw_enter_instance(sc, st, stack, world, inst_id);
         };
 
         bool progress = false;

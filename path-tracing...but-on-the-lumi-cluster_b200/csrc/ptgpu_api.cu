@@ -166,6 +166,7 @@ struct ptgpu_ctx
     // per frame
     DevBuf<RefSubframe> subframes;
     DevBuf<uint2> dyn_range;
+    DevBuf<float4> dyn_union;       // per subframe: world box (lo, hi) around all per-frame instances it sees
     size_t n_subframes = 0, n_dyn = 0;
     bool have_frame = false, frame_has_ref_tlas = false;
     std::vector<uint8_t> staging;   // pinned-size-agnostic host staging for per-frame uploads
@@ -244,7 +245,7 @@ Scene make_scene(ptgpu_ctx* ctx)
     s.instances = ctx->instances.p;
     s.subframes = ctx->subframes.p;
     s.wnodes = ctx->wnodes.p; s.wtris = ctx->wtris.p; s.wblas = ctx->wblas.p; s.winst = ctx->winst.p;
-    s.wtlas = ctx->wtlas.p; s.dyn_range = ctx->dyn_range.p;
+    s.wtlas = ctx->wtlas.p; s.dyn_range = ctx->dyn_range.p; s.dyn_union = ctx->dyn_union.p;
     s.cwnodes = ctx->cwnodes.p; s.cwtris = ctx->cwtris.p; s.cw_inst_index = ctx->cw_inst_index.p;
     s.cw_tlas_root = ctx->host ? ctx->host->wide.cw_tlas_root : 0u;
     s.flat_root = ctx->flat && ctx->have_flat ? ctx->flat_root : 0xFFFFFFFFu;
@@ -501,12 +502,14 @@ int upload_frame_common(ptgpu_ctx* ctx, const ptgpu_subframe* subframes, size_t 
     const size_t sz_dyn = n_dyn * sizeof(RefInstance);
     const size_t sz_rng = n_subframes * sizeof(uint2);
     const size_t sz_win = n_dyn * sizeof(WideInstance);
+    const size_t sz_uni = n_subframes * 2 * sizeof(float4);
     // the previous frame's copies must have left the staging block
     CK(cudaStreamSynchronize(ctx->stream));
-    uint8_t* st = (uint8_t*)pinned_staging(ctx, sz_sub + sz_dyn + sz_rng + sz_win + 64);
+    uint8_t* st = (uint8_t*)pinned_staging(ctx, sz_sub + sz_dyn + sz_rng + sz_win + sz_uni + 128);
     if(!st) return fail(ctx, "pinned staging allocation failed");
     CK(ctx->subframes.reserve(n_subframes));
     CK(ctx->dyn_range.reserve(n_subframes));
+    CK(ctx->dyn_union.reserve(2 * n_subframes));
     if(ctx->instances.cap < ctx->n_static + n_dyn)
     {   // grow, keeping the static part
         DevBuf<RefInstance> nb; CK(nb.reserve(ctx->n_static + n_dyn + 64));
@@ -519,6 +522,7 @@ int upload_frame_common(ptgpu_ctx* ctx, const ptgpu_subframe* subframes, size_t 
         ctx->winst.release(); ctx->winst = wb;
     }
     size_t off = 0;
+    const WideInstance* wi_host = nullptr;
     memcpy(st + off, subframes, sz_sub);
     CK(cudaMemcpyAsync(ctx->subframes.p, st + off, sz_sub, cudaMemcpyHostToDevice, ctx->stream));
     off += sz_sub;
@@ -532,10 +536,30 @@ int upload_frame_common(ptgpu_ctx* ctx, const ptgpu_subframe* subframes, size_t 
             if(!make_wide_instance(ctx->host->wide, dyn[i], (uint32_t)(ctx->n_static + i), wi[i]))
                 return fail(ctx, "dynamic instance %zu references an unknown BLAS (node_offset %u)", i, dyn[i].blas.node_offset);
         CK(cudaMemcpyAsync(ctx->winst.p + ctx->n_static, wi, sz_win, cudaMemcpyHostToDevice, ctx->stream));
+        wi_host = wi;
         off = ((off + 15) & ~size_t(15)) + sz_win;
     }
     memcpy(st + off, ranges.data(), sz_rng);
     CK(cudaMemcpyAsync(ctx->dyn_range.p, st + off, sz_rng, cudaMemcpyHostToDevice, ctx->stream));
+    off = (off + sz_rng + 15) & ~size_t(15);
+    {   // one box per subframe around everything its per-frame instances can cover: a query that misses it
+        // (most bounce and shadow rays) skips the per-instance box tests at its start (cw_begin)
+        float4* un = (float4*)(st + off);
+        for(size_t i = 0; i < n_subframes; ++i)
+        {
+            float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+            const uint32_t p = ranges[i].x, a = ranges[i].y & 0xFFFFFu, len = ranges[i].y >> 20;
+            for(uint32_t k = 0; k < p + len; ++k)
+            {
+                const WideInstance& w = wi_host[k < p ? k : a + (k - p)];
+                lo[0] = std::min(lo[0], w.lo.x); lo[1] = std::min(lo[1], w.lo.y); lo[2] = std::min(lo[2], w.lo.z);
+                hi[0] = std::max(hi[0], w.hi.x); hi[1] = std::max(hi[1], w.hi.y); hi[2] = std::max(hi[2], w.hi.z);
+            }
+            un[2 * i] = make_float4(lo[0], lo[1], lo[2], 0.0f);
+            un[2 * i + 1] = make_float4(hi[0], hi[1], hi[2], 0.0f);
+        }
+        CK(cudaMemcpyAsync(ctx->dyn_union.p, un, sz_uni, cudaMemcpyHostToDevice, ctx->stream));
+    }
     ctx->n_subframes = n_subframes;
     ctx->n_dyn = n_dyn;
     ctx->have_frame = true;
@@ -612,7 +636,7 @@ void ptgpu_destroy(ptgpu_ctx* ctx)
     ctx->ref_nodes.release(); ctx->ref_links.release(); ctx->indices.release();
     ctx->pos.release(); ctx->normal.release(); ctx->albedo.release(); ctx->material.release();
     ctx->instances.release(); ctx->wnodes.release(); ctx->wtris.release(); ctx->wblas.release();
-    ctx->winst.release(); ctx->wtlas.release(); ctx->cwnodes.release(); ctx->cwtris.release(); ctx->shade_tris.release(); ctx->cw_inst_index.release(); ctx->subframes.release(); ctx->dyn_range.release();
+    ctx->winst.release(); ctx->wtlas.release(); ctx->cwnodes.release(); ctx->cwtris.release(); ctx->shade_tris.release(); ctx->cw_inst_index.release(); ctx->subframes.release(); ctx->dyn_range.release(); ctx->dyn_union.release();
     ctx->out_bgra.release(); ctx->out_bmp.release(); ctx->out_rgb.release(); ctx->counters.release(); ctx->rect_bgra.release();
     ctx->mega_state.release(); ctx->wave_mem.release(); ctx->wave_flag.release();
     if(ctx->wave_flag_host) cudaFreeHost(ctx->wave_flag_host);

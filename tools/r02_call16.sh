@@ -1,0 +1,6 @@
+set -x
+P="/root/repo/path-tracing...but-on-the-lumi-cluster_b200"
+for v in _p00 _p10 _p01 _p11 _p12; do
+  echo "=== variant libptgpu$v.so" | tee -a gpurun_out/r02_ab16.log
+  PTGPU_LIB="$P/libptgpu$v.so" timeout 600 python tools/ab_frames.py --frames 0 520 1400 --configs "flat=1" --check 2>&1 | grep -v "^flat scene" | tee -a gpurun_out/r02_ab16.log
+done
