@@ -10,6 +10,7 @@
 // passed the box test, so a node visit pushes at most two entries and needs no distance sort —
 // children are stored in octant order and visited in (slot XOR ray octant) order.
 #pragma once
+#include <type_traits>
 #include "pt_scene.cuh"
 #include "pt_trav_links.cuh"
 #include "pt_wide.cuh"
@@ -27,30 +28,42 @@ namespace pt {
 // mix of depths), the rest in local memory. ncu on the all-local version: the loads of the stack top
 // and of the pending-triangle list were the top three stall sites of wf_trace_cw (25 % of samples).
 #ifndef CW_SM_STACK_N
-#define CW_SM_STACK_N 14
+#define CW_SM_STACK_N 7
 #endif
 constexpr int CW_SM_STACK = CW_SM_STACK_N;
+// Both also hold the query's closest-hit record (barycentrics, instance, primitive | back_face << 31) in two
+// entries behind the stack: it is written a few times per query and read once, so it has no business in
+// registers that the box test could use (wf_trace_cw_kernel: 64 per thread).
+#define CW_NO_HIT 0xFFFFFFFFu
 struct LocalStack
 {
-    uint2* p;
+    uint2* p;       // CW_STACK + 2 entries
     PT_D void set(int i, uint2 v) { p[i] = v; }
     PT_D uint2 get(int i) const { return p[i]; }
+    PT_D void hit_set(float u, float v, uint32_t inst, uint32_t prim_bf) { p[CW_STACK] = make_uint2(__float_as_uint(u), __float_as_uint(v)); p[CW_STACK + 1] = make_uint2(inst, prim_bf); }
+    PT_D void hit_clear() { p[CW_STACK] = make_uint2(0u, 0u); p[CW_STACK + 1] = make_uint2(CW_NO_HIT, 0u); }
+    PT_D uint2 hit_uv() const { return p[CW_STACK]; }
+    PT_D uint2 hit_id() const { return p[CW_STACK + 1]; }
 };
 struct HybridStack
 {
-    uint2* sm;      // &shared[0][thread]
+    uint2* sm;      // &shared[0][thread]; CW_SM_STACK + 2 rows
     uint2* lo;      // overflow (local memory)
     int stride;     // threads per block
     PT_D void set(int i, uint2 v) { if(i < CW_SM_STACK) sm[i * stride] = v; else lo[i - CW_SM_STACK] = v; }
     PT_D uint2 get(int i) const { return i < CW_SM_STACK ? sm[i * stride] : lo[i - CW_SM_STACK]; }
+    PT_D void hit_set(float u, float v, uint32_t inst, uint32_t prim_bf) { sm[CW_SM_STACK * stride] = make_uint2(__float_as_uint(u), __float_as_uint(v)); sm[(CW_SM_STACK + 1) * stride] = make_uint2(inst, prim_bf); }
+    PT_D void hit_clear() { sm[CW_SM_STACK * stride] = make_uint2(0u, 0u); sm[(CW_SM_STACK + 1) * stride] = make_uint2(CW_NO_HIT, 0u); }
+    PT_D uint2 hit_uv() const { return sm[CW_SM_STACK * stride]; }
+    PT_D uint2 hit_id() const { return sm[(CW_SM_STACK + 1) * stride]; }
 };
 
 // Per-query traversal state. Kept as small as the algorithm allows: wf_trace_cw_kernel runs at 64 registers
 // (8 blocks per SM), and every value held here across the box test is one the test cannot use. So the state
 // does NOT hold the world-space ray (o and idir are the world ray while outside an instance; on the rare exit
 // from one — <= 7 per-frame instances — the ray is read again from where the caller keeps it, see the `World`
-// argument of the functions below), nor the sign bits (they follow from the octant), nor the subframe, nor a
-// hit distance of its own: with a hit recorded (inst != CW_NO_HIT) the hit distance IS tmax.
+// argument of the functions below), nor the sign bits (they follow from the octant), nor the subframe, nor the
+// closest-hit record (it lives with the stack; `hit` only says that there is one, and its distance IS tmax).
 struct CwState
 {
     v3 o, idir;         // current space (world or instance): origin and clamped 1/direction
@@ -60,23 +73,21 @@ struct CwState
     float tmin, tmax;
     uint2 ngroup, tgroup;
     int sp;
-    bool in_blas, any;
+    bool in_blas, any, hit;
     uint32_t cur_inst;
-    float u, v;         // closest hit so far: barycentrics, (instance, primitive), facing; its distance is tmax
-    uint32_t inst, prim;
-    bool back_face;
 #ifdef WF_STATS
     uint32_t n_nodes = 0, n_tris = 0;   // census builds: node tests and triangle tests of this query
 #endif
-    PT_D bool has_hit() const { return inst != 0xFFFFFFFFu; }
-    PT_D Hit result() const
+    template<class Stack>
+    PT_D Hit result(const Stack& stack) const
     {
+        const uint2 uv = stack.hit_uv(), id = stack.hit_id();
         Hit h;
-        h.t = has_hit() ? tmax : -1.0f; h.u = u; h.v = v; h.inst = inst; h.prim = prim; h.back_face = back_face;
+        h.t = hit ? tmax : -1.0f; h.u = __uint_as_float(uv.x); h.v = __uint_as_float(uv.y);
+        h.inst = id.x; h.prim = id.y & 0x7FFFFFFFu; h.back_face = (id.y >> 31) != 0u;
         return h;
     }
 };
-#define CW_NO_HIT 0xFFFFFFFFu
 
 // Where the world-space ray of a query lives while the state does not hold it. The plain traversal keeps it in
 // registers (it has no register budget to meet); wf_trace_cw_kernel reads it back from the path-state pool.
@@ -128,6 +139,26 @@ PT_D void cw_set_space(CwState& st, v3 o, v3 d)
 // slots; the XU pipe is busy but not the limiter.
 PT_D float u8f(uint32_t w, int j) { return (float)((w >> (8 * j)) & 0xFFu); }
 
+// Byte j of w as the float 32768 + b, built by ONE PRMT on the ALU pipe (no XU instruction): the byte lands in
+// bits 8..15 of 0x47000000 = 2^15, where one unit of the byte is 2^8 ulp, so the value is exact. The slab offset
+// of such an axis carries -32768 * scale (cw_intersect_node); folding at 2^15 instead of the 2^23 of the earlier
+// experiment costs 2^-9 of a grid cell in rounding instead of half a cell: no box padding. `magic` = 0x47000000
+// comes from the constant bank (Scene::cw_magic) so that PRMT takes the byte selector as its immediate.
+#ifndef CW_MAGIC
+#define CW_MAGIC 1      // bit mask of the axes converted this way: 1 x, 2 y, 4 z (measured: x alone is best)
+#endif
+template<int AXIS, int J>
+PT_D float u8f_axis(uint32_t w, uint32_t magic)
+{
+    if(CW_MAGIC & (1 << AXIS))
+    {
+        uint32_t r;
+        asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(w), "r"(magic), "n"(0x7604 | (J << 4)));
+        return __uint_as_float(r);
+    }
+    return u8f(w, J);
+}
+
 // Top levels of the flat BVH staged in shared memory (north_star: "staging the top levels in shared memory
 // and leaving the rest to L2"): nodes [base, base + n) of the node array are also at sm[5 * (index - base)].
 struct TopLevels
@@ -141,7 +172,7 @@ constexpr uint32_t CW_TOP_NODES = 96;   // 7.5 KB per block
 // leaf group (leaf payloads whose box was hit).
 template<bool TOP>
 PT_D void cw_intersect_node(const float4* __restrict__ nodes, uint32_t node_index, const CwState& st,
-                            uint2& ngroup, uint2& tgroup, const TopLevels& top)
+                            uint2& ngroup, uint2& tgroup, const TopLevels& top, uint32_t magic)
 {
     float4 n0, n1, n2, n3, n4;
     if(TOP && node_index - top.base < top.n)
@@ -159,7 +190,10 @@ PT_D void cw_intersect_node(const float4* __restrict__ nodes, uint32_t node_inde
     const float sy = __uint_as_float((uint32_t)(((int)(ew << 16) >> 24) + 127) << 23);
     const float sz = __uint_as_float((uint32_t)(((int)(ew << 8) >> 24) + 127) << 23);
     const float ax = sx * st.idir.x, ay = sy * st.idir.y, az = sz * st.idir.z;
-    const float ox = (n0.x - st.o.x) * st.idir.x, oy = (n0.y - st.o.y) * st.idir.y, oz = (n0.z - st.o.z) * st.idir.z;
+    float ox = (n0.x - st.o.x) * st.idir.x, oy = (n0.y - st.o.y) * st.idir.y, oz = (n0.z - st.o.z) * st.idir.z;
+    if(CW_MAGIC & 1) ox = fmaf(-32768.0f, ax, ox);
+    if(CW_MAGIC & 2) oy = fmaf(-32768.0f, ay, oy);
+    if(CW_MAGIC & 4) oz = fmaf(-32768.0f, az, oz);
     const bool nx = !(st.oct_inv4 & 4u), ny = !(st.oct_inv4 & 2u), nz = !(st.oct_inv4 & 1u);
     // Boxes are culled against a slightly longer ray than the triangles: the box arithmetic rounds, so
     // with the exact tmax a node holding a hit a few ulp closer than the current one could be skipped or
@@ -180,17 +214,18 @@ PT_D void cw_intersect_node(const float4* __restrict__ nodes, uint32_t node_inde
         const uint32_t x_near = nx ? qhx : qlx, x_far = nx ? qlx : qhx;
         const uint32_t y_near = ny ? qhy : qly, y_far = ny ? qly : qhy;
         const uint32_t z_near = nz ? qhz : qlz, z_far = nz ? qlz : qhz;
-        #pragma unroll
-        for(int j = 0; j < 4; ++j)
-        {
-            const float t0x = fmaf(u8f(x_near, j), ax, ox), t1x = fmaf(u8f(x_far, j), ax, ox);
-            const float t0y = fmaf(u8f(y_near, j), ay, oy), t1y = fmaf(u8f(y_far, j), ay, oy);
-            const float t0z = fmaf(u8f(z_near, j), az, oz), t1z = fmaf(u8f(z_far, j), az, oz);
+        auto child = [&](auto jc) {
+            constexpr int j = decltype(jc)::value;
+            const float t0x = fmaf(u8f_axis<0, j>(x_near, magic), ax, ox), t1x = fmaf(u8f_axis<0, j>(x_far, magic), ax, ox);
+            const float t0y = fmaf(u8f_axis<1, j>(y_near, magic), ay, oy), t1y = fmaf(u8f_axis<1, j>(y_far, magic), ay, oy);
+            const float t0z = fmaf(u8f_axis<2, j>(z_near, magic), az, oz), t1z = fmaf(u8f_axis<2, j>(z_far, magic), az, oz);
             const float cmin = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, st.tmin));
             const float cmax = fminf(fminf(t1x, t1y), fminf(t1z, tmax_box));
             // every slot holds a real child or an inverted box: no validity mask (the shift uses the low 5 bits)
             if(cmin <= cmax) hitmask |= 1u << ((bit_index4 >> (8 * j)) & 31u);
-        }
+        };
+        child(std::integral_constant<int, 0>{}); child(std::integral_constant<int, 1>{});
+        child(std::integral_constant<int, 2>{}); child(std::integral_constant<int, 3>{});
     }
     ngroup.x = __float_as_uint(n1.x);
     ngroup.y = (hitmask & 0xFF000000u) | (ew >> 24);
@@ -219,8 +254,8 @@ template<bool PARKED, class Stack>
 PT_D void cw_begin(const Scene& sc, CwState& st, Stack& stack, uint32_t subframe, v3 ro, v3 rd,
                    float tmin, float tmax, bool any)
 {
-    st.tmin = tmin; st.tmax = tmax; st.any = any;
-    st.u = 0.0f; st.v = 0.0f; st.inst = CW_NO_HIT; st.prim = 0; st.back_face = false;
+    st.tmin = tmin; st.tmax = tmax; st.any = any; st.hit = false;
+    stack.hit_clear();
     st.sp = 0; st.in_blas = false; st.cur_inst = 0; st.axis = 2; st.S = mk3(0, 0, 1);
     cw_set_space(st, ro, rd);
     const uint2 r = __ldg(sc.dyn_range + subframe);
@@ -301,7 +336,8 @@ PT_D void cw_enter_instance(const Scene& sc, CwState& st, Stack& stack, const Wo
 }
 
 // One triangle of the leaf group (ray_query_test_triangle, ray_query.hh:225-246)
-PT_D void cw_test_triangle(const Scene& sc, CwState& st, uint32_t tri)
+template<class Stack>
+PT_D void cw_test_triangle(const Scene& sc, CwState& st, Stack& stack, uint32_t tri)
 {
     const float4* tp = sc.cwtris + 3 * (size_t)tri;
     const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
@@ -319,12 +355,17 @@ PT_D void cw_test_triangle(const Scene& sc, CwState& st, uint32_t tri)
     // which swaps front and back); BLAS triangles belong to the instance the ray is in (their b.w is 0)
     const uint32_t bw = __float_as_uint(b.w);
     const uint32_t inst = st.cur_inst == CW_FLAT_INST ? (bw & 0x7FFFFFFFu) : st.cur_inst;
-    const bool closer = t < st.tmax;
-    const bool tie = st.has_hit() && t == st.tmax &&
-        (inst < st.inst || (inst == st.inst && prim < st.prim));
-    if(ok && t > st.tmin && (closer || tie))
+    if(!(ok && t > st.tmin)) return;
+    bool accept = t < st.tmax;
+    if(!accept && st.hit && t == st.tmax)
+    {   // exact tie with the recorded hit
+        const uint2 id = stack.hit_id();
+        accept = inst < id.x || (inst == id.x && prim < (id.y & 0x7FFFFFFFu));
+    }
+    if(accept)
     {
-        st.u = u; st.v = v; st.inst = inst; st.prim = prim; st.back_face = bf != ((bw >> 31) != 0u);
+        stack.hit_set(u, v, inst, prim | ((bf != ((bw >> 31) != 0u)) ? 0x80000000u : 0u));
+        st.hit = true;
         st.tmax = t;
         if(st.any) { st.sp = 0; st.ngroup.y = 0u; st.tgroup.y = 0u; }
     }
@@ -346,7 +387,7 @@ PT_D void cw_node_phase(const Scene& sc, CwState& st, Stack& stack, const TopLev
 #ifdef WF_STATS
         st.n_nodes++;
 #endif
-        cw_intersect_node<TOP>(sc.cwnodes, base + rel, st, st.ngroup, st.tgroup, top);
+        cw_intersect_node<TOP>(sc.cwnodes, base + rel, st, st.ngroup, st.tgroup, top, sc.cw_magic);
     }
     else
     {   // the entry popped last was a leaf group
@@ -394,7 +435,7 @@ template<bool ANY>
 PT_D bool trace_cw(const Scene& sc, uint32_t subframe, v3 origin, v3 dir, float tmin, float tmax, Hit& hit,
                    uint32_t* census = nullptr)
 {
-    uint2 stack_mem[CW_STACK];
+    uint2 stack_mem[CW_STACK + 2];
     LocalStack stack{stack_mem};
     CwState st;
     const WorldRayRegs world{origin, dir, subframe};
@@ -409,13 +450,13 @@ PT_D bool trace_cw(const Scene& sc, uint32_t subframe, v3 origin, v3 dir, float 
             {
                 const uint32_t bit = 31u - (uint32_t)__clz(st.tgroup.y);
                 st.tgroup.y &= ~(1u << bit);
-                cw_test_triangle(sc, st, st.tgroup.x + bit);
+                cw_test_triangle(sc, st, stack, st.tgroup.x + bit);
             }
         }
         else if(st.tgroup.y) cw_instance_phase(sc, st, stack, world);
         if(!cw_pop_phase(sc, st, stack, world)) break;
     }
-    hit = st.result();
+    hit = st.result(stack);
 #ifdef WF_STATS
     if(census) { census[0] = st.n_nodes; census[1] = st.n_tris; }
 #endif

@@ -109,6 +109,7 @@ struct Scene
     uint32_t flat_root;
     uint32_t flat_top;              // nodes [flat_root, flat_root + flat_top) are its top levels, breadth-first
     uint32_t dyn_first;             // flat scene: a query enters the per-frame instances before the static world
+    uint32_t cw_magic;              // 0x47000000 (2^15 as a float), see u8f_axis (pt_cwbvh.cuh)
     // ray-sort grid (pt_wave.cuh): cell = (p - key_lo) * key_scale, 32 x 8 x 32 cells over the static scene
     float key_lo[3], key_scale[3];
     uint32_t n_static;

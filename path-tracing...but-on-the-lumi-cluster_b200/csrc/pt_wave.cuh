@@ -324,7 +324,7 @@ constexpr int CW_PEND = CW_PEND_N;
 // spills) by 7 %; with the flat scene the kernel waits on memory more (L1 hit 47-65 %, long_scoreboard the top
 // stall in the bounce rounds) and 8 blocks = 32 warps win 3.5 % (32 B spill stores, 76 B loads).
 #ifndef WF_CW_BLOCKS
-#define WF_CW_BLOCKS 8
+#define WF_CW_BLOCKS 9
 #endif
 
 // The world-space ray of the lane's query, read back from the path-state pool on the rare occasions the
@@ -364,7 +364,7 @@ wf_trace_cw_kernel(Scene sc, RenderJob job, WaveBuffers wb)
 
     bool active = false;
     uint32_t slot = 0;
-    __shared__ uint2 s_stack[CW_SM_STACK][WF_TRACE_THREADS];
+    __shared__ uint2 s_stack[CW_SM_STACK + 2][WF_TRACE_THREADS];   // + the closest-hit record (pt_cwbvh.cuh)
     __shared__ uint2 s_pend[CW_PEND][WF_TRACE_THREADS];
     uint2 stack_overflow[CW_STACK - CW_SM_STACK];
     HybridStack stack{&s_stack[0][threadIdx.x], stack_overflow, WF_TRACE_THREADS};
@@ -442,12 +442,13 @@ wf_trace_cw_kernel(Scene sc, RenderJob job, WaveBuffers wb)
                     if(np == 0)
                     {   // query complete: write the result
                         active = false;
-                        if(st.any) wb.visible[slot] = st.has_hit() ? 0u : 1u;
+                        if(st.any) wb.visible[slot] = st.hit ? 0u : 1u;
                         else
                         {
-                            const float t = st.has_hit() ? st.tmax : -1.0f;
-                            wb.hit[slot] = make_float4(t, st.u, st.v, __uint_as_float(st.inst));
-                            wb.hit_prim[slot] = st.prim | (st.back_face ? 0x80000000u : 0u);
+                            const float t = st.hit ? st.tmax : -1.0f;
+                            const uint2 uv = stack.hit_uv(), id = stack.hit_id();
+                            wb.hit[slot] = make_float4(t, __uint_as_float(uv.x), __uint_as_float(uv.y), __uint_as_float(id.x));
+                            wb.hit_prim[slot] = id.y;
                             wb.status[slot] = (t > 0.0f && t < 1e3f) ? WF_ST_NEAR : WF_ST_FAR;
                         }
                     }
@@ -506,8 +507,8 @@ wf_trace_cw_kernel(Scene sc, RenderJob job, WaveBuffers wb)
             const uint32_t bit = 31u - (uint32_t)__clz(g.y);
             g.y &= ~(1u << bit);
             if(g.y) pend[(np - 1) * WF_TRACE_THREADS] = g; else np--;
-            cw_test_triangle(sc, st, g.x + bit);
-            if(st.any && st.has_hit()) np = 0; // any hit ends a shadow query (sp and groups are cleared)
+            cw_test_triangle(sc, st, stack, g.x + bit);
+            if(st.any && st.hit) np = 0; // any hit ends a shadow query (sp and groups are cleared)
         };
         auto enter_step = [&]() {
             // enter one instance of the group; the rest of the group and the world-space ray constants are

@@ -251,6 +251,7 @@ Scene make_scene(ptgpu_ctx* ctx)
     s.flat_root = ctx->flat && ctx->have_flat ? ctx->flat_root : 0xFFFFFFFFu;
     s.flat_top = ctx->flat_top;
     s.dyn_first = (uint32_t)ctx->dyn_first;
+    s.cw_magic = 0x47000000u;
     for(int a = 0; a < 3; ++a) { s.key_lo[a] = ctx->key_lo[a]; s.key_scale[a] = ctx->key_scale[a]; }
     s.n_static = (uint32_t)ctx->n_static;
     s.n_subframes = (uint32_t)ctx->n_subframes;
