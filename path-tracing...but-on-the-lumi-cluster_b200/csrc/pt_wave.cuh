@@ -87,6 +87,11 @@ PT_D bool slot_pixel(const WaveBuffers& wb, const RenderJob& job, uint32_t slot,
     return lx < job.w && ly < job.h;
 }
 
+#ifndef WF_SHADE_PREFETCH
+#define WF_SHADE_PREFETCH 1
+#endif
+PT_D void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
+
 // Warp-aggregated append; must be reached by all 32 lanes of the warp.
 PT_D void wf_append(uint32_t* q, uint32_t* count, bool pred, uint32_t val)
 {
@@ -125,6 +130,46 @@ PT_D void wf_append_block(uint32_t* q, uint32_t* count, bool pred, uint32_t val,
         const uint32_t pos = base + __popc(m & ((1u << lane) - 1u));
         q[pos] = val;
         if(q_key) q_key[pos] = key;
+    }
+    __syncthreads();
+}
+
+// Two block-aggregated appends behind one set of barriers (the shade kernels append a bounce and a shadow ray
+// per slot: ncu put 10 % of wf_shade<NEAR>'s stall samples on the six barriers of two separate appends).
+// `s_tmp` is 2 * (WARPS + 1) words.
+template<int WARPS>
+PT_D void wf_append2_block(uint32_t* q0, uint32_t* count0, bool pred0, uint32_t val0, uint32_t* key0, uint32_t k0,
+                           uint32_t* q1, uint32_t* count1, bool pred1, uint32_t val1, uint32_t* key1, uint32_t k1,
+                           uint32_t* s_tmp)
+{
+    const unsigned m0 = __ballot_sync(0xFFFFFFFFu, pred0), m1 = __ballot_sync(0xFFFFFFFFu, pred1);
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    if(lane == 0u) { s_tmp[warp] = (uint32_t)__popc(m0); s_tmp[WARPS + 1 + warp] = (uint32_t)__popc(m1); }
+    __syncthreads();
+    if(threadIdx.x < 2)
+    {
+        uint32_t* t = s_tmp + threadIdx.x * (WARPS + 1);
+        uint32_t total = 0;
+        #pragma unroll
+        for(int k = 0; k < WARPS; ++k) total += t[k];
+        t[WARPS] = total ? atomicAdd(threadIdx.x ? count1 : count0, total) : 0u;
+    }
+    __syncthreads();
+    if(pred0)
+    {
+        uint32_t base = s_tmp[WARPS];
+        for(unsigned k = 0; k < warp; ++k) base += s_tmp[k];
+        const uint32_t pos = base + __popc(m0 & ((1u << lane) - 1u));
+        q0[pos] = val0;
+        if(key0) key0[pos] = k0;
+    }
+    if(pred1)
+    {
+        uint32_t base = s_tmp[2 * WARPS + 1];
+        for(unsigned k = 0; k < warp; ++k) base += s_tmp[WARPS + 1 + k];
+        const uint32_t pos = base + __popc(m1 & ((1u << lane) - 1u));
+        q1[pos] = val1;
+        if(key1) key1[pos] = k1;
     }
     __syncthreads();
 }
@@ -570,7 +615,7 @@ wf_trace_cw_kernel(Scene sc, RenderJob job, WaveBuffers wb)
         }
         // -- ENTER block -----------------------------------------------------------------------------------
         {
-            advance();
+            advance();   // (measured: without this second pop opportunity per iteration the frame is 4.6 % slower)
             const bool w = wants_enter();
             if(__popc(__ballot_sync(0xFFFFFFFFu, w)) >= job.xform_threshold)
             {
@@ -712,11 +757,18 @@ wf_shade_kernel(Scene sc, RenderJob job, WaveBuffers wb)
 {
     const uint32_t n = FAR ? wb.cnt->n_far : wb.cnt->n_near;
     const uint32_t* q = FAR ? wb.q_far : wb.q_near;
-    __shared__ uint32_t s_tmp[2][5];
+    __shared__ uint32_t s_tmp[2 * 5];
     const uint32_t rounded = (n + 127u) & ~127u;   // whole blocks (block-aggregated appends below)
-    for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < rounded; i += gridDim.x * blockDim.x)
+    const uint32_t step = gridDim.x * blockDim.x;
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t slot_ahead = i < n ? q[i] : WF_INVALID;
+    for(; i < rounded; i += step)
     {
-        const uint32_t slot = i < n ? q[i] : WF_INVALID;
+        const uint32_t slot = slot_ahead;
+        // The slot of the NEXT iteration is fetched now and its path state pulled into L2 half-way through this
+        // one: the kernel is bound by the latency of its dependent loads (queue -> state -> hit -> shading
+        // record: issue slots 37 % busy, long_scoreboard the top stall), not by bandwidth (2.2 of 6.5 TB/s).
+        slot_ahead = (i + step < n) ? q[i + step] : WF_INVALID;
         bool push_ext = false, push_shadow = false, push_new = false;
         uint32_t key_ext = 0u, key_shadow = 0u;
         if(slot != WF_INVALID)
@@ -754,6 +806,15 @@ wf_shade_kernel(Scene sc, RenderJob job, WaveBuffers wb)
             hit.prim = hp & 0x7FFFFFFFu; hit.back_face = (hp & 0x80000000u) != 0u;
             HitInfo info;
             shade_hit(sc, light, hit, ray_o, ray_d, info);
+#if WF_SHADE_PREFETCH
+            if(slot_ahead != WF_INVALID)
+            {
+                prefetch_l2(wb.cursor + slot_ahead); prefetch_l2(wb.ray_o + slot_ahead); prefetch_l2(wb.ray_d + slot_ahead);
+                prefetch_l2(wb.atten + slot_ahead); prefetch_l2(wb.contrib + slot_ahead); prefetch_l2(wb.rng + slot_ahead);
+                prefetch_l2(wb.nee + slot_ahead); prefetch_l2(wb.hit + slot_ahead); prefetch_l2(wb.hit_prim + slot_ahead);
+                prefetch_l2(wb.visible + slot_ahead); prefetch_l2(wb.shadow_d + slot_ahead);
+            }
+#endif
 
             const float mis_pdf = bsdf_pdf < 0.0f ? -bsdf_pdf :
                 (info.nee_pdf * info.nee_pdf + bsdf_pdf * bsdf_pdf) / bsdf_pdf;
@@ -817,10 +878,10 @@ wf_shade_kernel(Scene sc, RenderJob job, WaveBuffers wb)
             }
         }
         uint32_t* keys = wb.sort ? wb.q_key : nullptr;
-        wf_append_block<4>(wb.q_trace + WF_SEG_SHADOW * (size_t)wb.seg_cap, &wb.cnt->n_seg[WF_SEG_SHADOW], push_shadow, slot | WF_SHADOW_BIT, s_tmp[0],
-                           keys ? keys + WF_SEG_SHADOW * (size_t)wb.seg_cap : nullptr, key_shadow);
-        wf_append_block<4>(wb.q_trace + WF_SEG_BOUNCE * (size_t)wb.seg_cap, &wb.cnt->n_seg[WF_SEG_BOUNCE], push_ext, slot, s_tmp[1],
-                           keys ? keys + WF_SEG_BOUNCE * (size_t)wb.seg_cap : nullptr, key_ext);
+        wf_append2_block<4>(wb.q_trace + WF_SEG_SHADOW * (size_t)wb.seg_cap, &wb.cnt->n_seg[WF_SEG_SHADOW], push_shadow, slot | WF_SHADOW_BIT,
+                            keys ? keys + WF_SEG_SHADOW * (size_t)wb.seg_cap : nullptr, key_shadow,
+                            wb.q_trace + WF_SEG_BOUNCE * (size_t)wb.seg_cap, &wb.cnt->n_seg[WF_SEG_BOUNCE], push_ext, slot,
+                            keys ? keys + WF_SEG_BOUNCE * (size_t)wb.seg_cap : nullptr, key_ext, s_tmp);
         // n_new is a flag (wf_generate only asks whether it is non-zero): a plain store, not an atomic per warp
         if(__any_sync(0xFFFFFFFFu, push_new) && (threadIdx.x & 31u) == 0u) wb.cnt->n_new = 1u;
     }
