@@ -251,7 +251,7 @@ PT_D bool sky_scattering(rng4& seed, const Light& light, v3 pos, v3 view, float 
     float ray_od = 0.0f, mie_od = 0.0f;
     v3 ray_sum = mk3(0, 0, 0), mie_sum = mk3(0, 0, 0);
     float l0 = tmin, l1 = tmax;
-    #pragma unroll 1
+    #pragma unroll 1   // (unrolled by 2: 104 registers, same time)
     for(int i = 0; i < PT_ATMO_PRIMARY; ++i)
     {
         float t = segment * (jitter.x + (float)i);

@@ -371,6 +371,9 @@ constexpr int CW_PEND = CW_PEND_N;
 #ifndef WF_CW_BLOCKS
 #define WF_CW_BLOCKS 9
 #endif
+#ifndef WF_TRI_BURST
+#define WF_TRI_BURST 4     // triangle steps per TRI block (2: +4.9 %, 3: +0.5 %, 6 and 16: +0.3 %; profiles/r02_trace_kernel_history.md)
+#endif
 
 // The world-space ray of the lane's query, read back from the path-state pool on the rare occasions the
 // traversal needs it again (entering or leaving one of the <= 7 per-frame instances: ~5 M times per frame
@@ -602,7 +605,7 @@ wf_trace_cw_kernel(Scene sc, RenderJob job, WaveBuffers wb)
             bool w = wants_tri();
             int n = __popc(__ballot_sync(0xFFFFFFFFu, w));
             #pragma unroll 1
-            for(int b = 0; b < 3 && n >= job.tri_threshold; ++b)
+            for(int b = 0; b < WF_TRI_BURST && n >= job.tri_threshold; ++b)
             {
 #ifdef WF_STATS
                 if(lane == 0) { atomicAdd(&wb.stats[8], 1ull); atomicAdd(&wb.stats[9], (unsigned long long)n); }
