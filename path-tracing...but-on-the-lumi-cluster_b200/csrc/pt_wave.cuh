@@ -645,6 +645,42 @@ wf_trace_cw_kernel(Scene sc, RenderJob job, WaveBuffers wb)
     }
 }
 
+// ---- reference point: the same queue traced by the plain single-ray loop, one thread per ray -------------
+// (ptgpu_set_option "plain_trace" = 1 for all rounds, 2 for the primary round only; what the warp scheduling
+// of wf_trace_cw_kernel is measured against, profiles/r02_trace_kernel_history.md)
+__global__ void __launch_bounds__(128)
+wf_trace_plain_kernel(Scene sc, RenderJob job, WaveBuffers wb)
+{
+    const uint32_t n_s0 = wb.cnt->n_seg[0], n_s1 = wb.cnt->n_seg[1], n_s2 = wb.cnt->n_seg[2];
+    const uint32_t n = n_s0 + n_s1 + n_s2;
+    const uint32_t* seg_bounce = wb.sort ? wb.q_sorted : wb.q_trace;
+    const uint32_t* seg_shadow = wb.sort ? wb.q_sorted + wb.seg_cap : wb.q_trace + 2 * (size_t)wb.seg_cap;
+    for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    {
+        const uint32_t e = i < n_s0 ? seg_bounce[i] : i - n_s0 < n_s1 ? wb.q_trace[wb.seg_cap + (i - n_s0)] : seg_shadow[i - n_s0 - n_s1];
+        if(e == WF_INVALID) continue;
+        const uint32_t slot = e & ~WF_SHADOW_BIT;
+        const bool shadow = (e & WF_SHADOW_BIT) != 0u;
+        const float4 fo = wb.ray_o[slot];
+        const float4 fd = shadow ? wb.shadow_d[slot] : wb.ray_d[slot];
+        const int sample = job.s_begin + wb.cursor[slot].x * job.s_stride;
+        const uint32_t subframe = sample < 0 ? 0u : (uint32_t)sample / (uint32_t)sc.samples_per_subframe;
+        Hit h;
+        if(shadow)
+        {
+            trace_cw<true>(sc, subframe, mk3(fo.x, fo.y, fo.z), mk3(fd.x, fd.y, fd.z), fo.w, PT_MAX_RAY_DIST, h);
+            wb.visible[slot] = h.t < 0.0f ? 1u : 0u;
+        }
+        else
+        {
+            trace_cw<false>(sc, subframe, mk3(fo.x, fo.y, fo.z), mk3(fd.x, fd.y, fd.z), fo.w, PT_MAX_RAY_DIST, h);
+            wb.hit[slot] = make_float4(h.t, h.u, h.v, __uint_as_float(h.inst));
+            wb.hit_prim[slot] = h.prim | (h.back_face ? 0x80000000u : 0u);
+            wb.status[slot] = (h.t > 0.0f && h.t < 1e3f) ? WF_ST_NEAR : WF_ST_FAR;
+        }
+    }
+}
+
 // ---- debug: re-trace every queue entry with the plain single-ray traversal and compare ---------------
 // (ptgpu_set_option "validate" = 1; counts and prints mismatches of the scheduled kernel)
 __global__ void wf_validate_kernel(Scene sc, RenderJob job, WaveBuffers wb, unsigned long long* mismatch)

@@ -133,6 +133,7 @@ struct ptgpu_ctx
     int flat = 1;                              // static instances as one world-space BVH (built at upload)
     int sort = 1;                              // wavefront: bounce and shadow rays sorted by octant + origin cell
     int top_smem = 0;                          // wavefront: top levels of the flat BVH staged in shared memory
+    int plain_trace = 0;                       // wavefront: 1 = every round, 2 = the primary round traced by the plain single-ray loop (reference point)
     int dyn_first = 1;                         // flat scene: per-frame instances are entered before the static world
 
     // static scene, reference layout
@@ -380,7 +381,8 @@ int launch_wave(ptgpu_ctx* ctx, const Scene& sc, RenderJob job)
             }
             wf_generate_kernel<<<sms * 4, 256, 0, st>>>(sc, job, wb);
             if(timed) cudaEventRecord(ctx->wave_events[4 * rounds + 1], st);
-            if(ctx->top_smem) wf_trace_cw_kernel<true><<<sms * WF_CW_BLOCKS, WF_TRACE_THREADS, 0, st>>>(sc, job, wb);
+            if(ctx->plain_trace == 1 || (ctx->plain_trace == 2 && rounds == 0)) wf_trace_plain_kernel<<<sms * 16, 128, 0, st>>>(sc, job, wb);
+            else if(ctx->top_smem) wf_trace_cw_kernel<true><<<sms * WF_CW_BLOCKS, WF_TRACE_THREADS, 0, st>>>(sc, job, wb);
             else wf_trace_cw_kernel<false><<<sms * WF_CW_BLOCKS, WF_TRACE_THREADS, 0, st>>>(sc, job, wb);
             if(timed) cudaEventRecord(ctx->wave_events[4 * rounds + 2], st);
             if(ctx->validate) wf_validate_kernel<<<sms * 8, 128, 0, st>>>(sc, job, wb, wb.stats + 39);
@@ -1186,6 +1188,7 @@ int ptgpu_set_option(ptgpu_ctx* ctx, const char* key, int64_t value)
         ctx->flat = (int)value; return 0; }
     if(!strcmp(key, "sort")) { if(value != 0 && value != 1) return fail(ctx, "sort must be 0 or 1"); ctx->sort = (int)value; return 0; }
     if(!strcmp(key, "dyn_first")) { if(value != 0 && value != 1) return fail(ctx, "dyn_first must be 0 or 1"); ctx->dyn_first = (int)value; return 0; }
+    if(!strcmp(key, "plain_trace")) { if(value < 0 || value > 2) return fail(ctx, "plain_trace must be 0, 1 or 2"); ctx->plain_trace = (int)value; return 0; }
     if(!strcmp(key, "top_smem")) { if(value != 0 && value != 1) return fail(ctx, "top_smem must be 0 or 1"); ctx->top_smem = (int)value; return 0; }
     if(!strcmp(key, "lanes")) { if(value < 1 || value > 4096 || (value & (value - 1))) return fail(ctx, "lanes must be a power of two in 1..4096"); ctx->max_lanes = (int)value; return 0; }
     if(!strcmp(key, "pool_budget_mb")) { if(value < 1) return fail(ctx, "pool_budget_mb must be positive"); ctx->pool_budget_bytes = (size_t)value << 20; return 0; }

@@ -21,7 +21,7 @@ import __graft_entry__ as ge  # noqa: E402
 
 
 # options a config does not name go back to these (options are sticky in a context)
-DEFAULTS = {"sort": 1, "dyn_first": 1, "top_smem": 0, "node_threshold": 16, "node_burst": -1, "tri_threshold": 8,
+DEFAULTS = {"sort": 1, "dyn_first": 1, "top_smem": 0, "plain_trace": 0, "node_threshold": 16, "node_burst": -1, "tri_threshold": 8,
             "xform_threshold": -1, "min_active": -1}
 
 
