@@ -1182,22 +1182,9 @@ bool build_wide_scene(
     auto emit_inst = [](const std::vector<uint32_t>& ids) -> uint32_t { return 0x80000000u | ids[0]; };
     uint32_t tstack = collapse_tree(ttree, 1, out.tlas, emit_inst);
     {
-        // compressed TLAS: without the world-space start instance, if the scene has one
-        if(CW_WORLD_START && n_static > 1)
-        {
-            uint32_t best_tris = 0;
-            for(size_t i = 0; i < n_static; ++i)
-            {
-                const ptgpu_float4* c = instances[i].transform.r;
-                const bool identity =
-                    c[0].x == 1.f && c[0].y == 0.f && c[0].z == 0.f && c[1].x == 0.f && c[1].y == 1.f && c[1].z == 0.f &&
-                    c[2].x == 0.f && c[2].y == 0.f && c[2].z == 1.f && c[3].x == 0.f && c[3].y == 0.f && c[3].z == 0.f;
-                const uint32_t tris = out.blas[out.instances[i].blas].tri_count;
-                if(identity && tris >= 1024u && tris > best_tris) { best_tris = tris; out.cw_world_inst = (uint32_t)i; }
-            }
-        }
+        // compressed TLAS over all static instances
         std::vector<Prim> cprims;
-        for(const Prim& pr : prims) if(pr.id != out.cw_world_inst) cprims.push_back(pr);
+        for(const Prim& pr : prims) cprims.push_back(pr);
         std::vector<TNode> ctree(1);
         ctree.reserve(2 * cprims.size());
         build_sah(cprims, 0, cprims.size(), ctree, 0);
@@ -1547,7 +1534,6 @@ uint64_t verify_wide_scene(const WideScene& ws, size_t n_static, std::string& er
         }
         std::vector<uint32_t> seen(n_static, 0);
         walk_cw(ws.cw_tlas_root, true, seen, 0, (uint32_t)n_static);
-        if(ws.cw_world_inst < n_static) seen[ws.cw_world_inst]++; // not a TLAS leaf: every query starts inside it
         for(uint32_t c : seen) if(c != 1) { fail("compressed TLAS: instance missing or duplicated"); break; }
     }
     return bad;

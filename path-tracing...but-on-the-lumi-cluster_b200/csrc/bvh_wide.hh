@@ -39,9 +39,6 @@ struct WideScene
     std::vector<uint32_t> cw_inst_index;
     std::vector<uint32_t> cw_blas_root; // per BLAS: root node index
     uint32_t cw_tlas_root = 0;
-    // the largest static instance with an identity transform (the terrain): every query starts inside it
-    // instead of meeting it as a TLAS leaf, so it costs no instance entry; 0xFFFFFFFF = none
-    uint32_t cw_world_inst = 0xFFFFFFFFu;
     uint32_t cw_max_stack = 0;          // group-stack entries a traversal can need
     bool from_meshes = false;           // BLASes built from triangles (ptgpu_upload_meshes), not recovered
 };
@@ -61,11 +58,6 @@ struct FlatScene
 
 constexpr int CW_WIDTH = 8;             // children per node
 constexpr int CW_LEAF_MAX = 1;          // triangles per leaf child (the encoding allows 3; measured 1: 245 ms, 2: 251, 3: 255 on frame 520)
-#ifndef CW_WORLD_START
-#define CW_WORLD_START 0             // 1: queries start inside the identity-transform terrain instance (no entry step).
-                                     // Measured: frame 0 60.7 -> 59.3 ms, but forest frames 210.6 -> 222.2 and 319.9 -> 325.0 ms:
-                                     // walking the terrain before the trees forgoes the short rays the tree hits give it. Off.
-#endif
 #ifndef CW_OPTIMAL_COLLAPSE
 #define CW_OPTIMAL_COLLAPSE 1        // cost-optimal (dynamic programming) collapse into 8-wide nodes; 0 = greedy
 #endif

@@ -269,7 +269,9 @@ def test_scheduled_traversal_equals_plain_traversal(frames):
             assert r.get_stat("wave_lanes") == 64 and r.get_stat("wave_rounds") <= 8
             # and the image does not depend on how the warps were scheduled
             r.set_option("validate", 0)
-            for opts in ({"node_threshold": 1, "tri_threshold": 1, "xform_threshold": 1}, {"node_burst": 1, "min_active": 1}, {"lanes": 8}):
+            # (plain_trace: the queues traced by the plain one-thread-per-ray loop instead of the scheduled kernel)
+            for opts in ({"node_threshold": 1, "tri_threshold": 1, "xform_threshold": 1}, {"node_burst": 1, "min_active": 1},
+                         {"plain_trace": 1}, {"plain_trace": 2}, {"lanes": 8}):
                 for k, v in opts.items():
                     r.set_option(k, v)
                 b, _ = r.render_rect(96, 240, 96, 64, 0, 64, 4, tonemap=False)
@@ -277,7 +279,8 @@ def test_scheduled_traversal_equals_plain_traversal(frames):
                     np.testing.assert_allclose(a, b, rtol=2e-5, atol=1e-7)
                 else:
                     assert np.array_equal(a, b), opts
-                for k, v in {"node_threshold": 16, "tri_threshold": 8, "xform_threshold": -1, "node_burst": -1, "min_active": -1, "lanes": 256}.items():
+                for k, v in {"node_threshold": 16, "tri_threshold": 8, "xform_threshold": -1, "node_burst": -1, "min_active": -1,
+                             "plain_trace": 0, "lanes": 256}.items():
                     r.set_option(k, v)
         finally:
             r.set_option("validate", 0)
