@@ -33,7 +33,7 @@ namespace pt {
 constexpr int CW_SM_STACK = CW_SM_STACK_N;
 // Both also hold the query's closest-hit record (barycentrics, instance, primitive | back_face << 31) in two
 // entries behind the stack: it is written a few times per query and read once, so it has no business in
-// registers that the box test could use (wf_trace_cw_kernel: 64 per thread).
+// registers that the box test could use (wf_trace_cw_kernel: 56 per thread).
 #define CW_NO_HIT 0xFFFFFFFFu
 struct LocalStack
 {
@@ -58,8 +58,8 @@ struct HybridStack
     PT_D uint2 hit_id() const { return sm[(CW_SM_STACK + 1) * stride]; }
 };
 
-// Per-query traversal state. Kept as small as the algorithm allows: wf_trace_cw_kernel runs at 64 registers
-// (8 blocks per SM), and every value held here across the box test is one the test cannot use. So the state
+// Per-query traversal state. Kept as small as the algorithm allows: wf_trace_cw_kernel runs at 56 registers
+// (9 blocks per SM), and every value held here across the box test is one the test cannot use. So the state
 // does NOT hold the world-space ray (o and idir are the world ray while outside an instance; on the rare exit
 // from one — <= 7 per-frame instances — the ray is read again from where the caller keeps it, see the `World`
 // argument of the functions below), nor the sign bits (they follow from the octant), nor the subframe, nor the

@@ -366,8 +366,10 @@ constexpr int WF_FETCH_CHUNK = WF_FETCH_CHUNK_N;
 constexpr int CW_PEND = CW_PEND_N;
 
 // Resident blocks per SM. With the instanced scene 7 (72 registers, no spills) beat 8 (64 registers, 110 B of
-// spills) by 7 %; with the flat scene the kernel waits on memory more (L1 hit 47-65 %, long_scoreboard the top
-// stall in the bounce rounds) and 8 blocks = 32 warps win 3.5 % (32 B spill stores, 76 B loads).
+// spills) by 7 %; with the flat scene the kernel waits on memory more and 8 blocks won 3.5 % in spite of the
+// spills. With the lean traversal state (pt_cwbvh.cuh: no world ray, sign bits, subframe or hit record in
+// registers) the kernel needs 56 registers without spills: 9 blocks = 36 warps, -8 % against the spilling
+// 64-register kernel. 10 blocks (48 registers) spill again: +8 %.
 #ifndef WF_CW_BLOCKS
 #define WF_CW_BLOCKS 9
 #endif
