@@ -721,7 +721,8 @@ struct CwEmitter
             if(ex < -126) ex = -126;
             // make sure 255 steps really cover the extent in float arithmetic
             while(n.box.lo[a] + 255.0f * std::ldexp(1.0f, ex) < n.box.hi[a]) ex++;
-            if(ex > 127) { err = "box extent too large to quantise"; return 0; }
+            // (59: the traversal adds the exponent to that of 1/d, up to 2^67, in integer arithmetic: pt_cwbvh.cuh)
+            if(ex > 59) { err = "box extent too large to quantise"; return 0; }
             e[a] = ex; scale[a] = std::ldexp(1.0f, ex);
         }
         uint8_t qlo[3][8] = {{0}}, qhi[3][8] = {{0}}, meta[8] = {0};

@@ -186,10 +186,12 @@ PT_D void cw_intersect_node(const float4* __restrict__ nodes, uint32_t node_inde
         n0 = __ldg(n); n1 = __ldg(n + 1); n2 = __ldg(n + 2); n3 = __ldg(n + 3); n4 = __ldg(n + 4);
     }
     const uint32_t ew = __float_as_uint(n0.w);
-    const float sx = __uint_as_float((uint32_t)(((int)(ew << 24) >> 24) + 127) << 23);
-    const float sy = __uint_as_float((uint32_t)(((int)(ew << 16) >> 24) + 127) << 23);
-    const float sz = __uint_as_float((uint32_t)(((int)(ew << 8) >> 24) + 127) << 23);
-    const float ax = sx * st.idir.x, ay = sy * st.idir.y, az = sz * st.idir.z;
+    // scale x 1/d as an integer add on the exponent field (three instructions fewer per node than decoding the
+    // scale and multiplying; same bits): |1/d| lies in [1, 1e20] (cw_set_space) and the builder keeps the
+    // exponents in [-126, 59] (bvh_wide.cu), so the sum never leaves the normal range
+    const float ax = __uint_as_float(__float_as_uint(st.idir.x) + (uint32_t)((((int)(ew << 24)) >> 1) & (int)0xFF800000));
+    const float ay = __uint_as_float(__float_as_uint(st.idir.y) + (uint32_t)((((int)(ew << 16)) >> 1) & (int)0xFF800000));
+    const float az = __uint_as_float(__float_as_uint(st.idir.z) + (uint32_t)((((int)(ew << 8)) >> 1) & (int)0xFF800000));
     float ox = (n0.x - st.o.x) * st.idir.x, oy = (n0.y - st.o.y) * st.idir.y, oz = (n0.z - st.o.z) * st.idir.z;
     if(CW_MAGIC & 1) ox = fmaf(-32768.0f, ax, ox);
     if(CW_MAGIC & 2) oy = fmaf(-32768.0f, ay, oy);

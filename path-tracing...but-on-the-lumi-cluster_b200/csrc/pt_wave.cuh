@@ -343,7 +343,10 @@ wf_generate_kernel(Scene sc, RenderJob job, WaveBuffers wb)
 }
 
 // ---- trace: persistent traversal kernel -----------------------------------------------------------
-constexpr int WF_TRACE_THREADS = 128;
+#ifndef WF_TRACE_THREADS_N
+#define WF_TRACE_THREADS_N 128     // (64 x 18 and 96 x 12 blocks per SM measured the same)
+#endif
+constexpr int WF_TRACE_THREADS = WF_TRACE_THREADS_N;
 #ifndef WF_FETCH_CHUNK_N
 #define WF_FETCH_CHUNK_N 64
 #endif
