@@ -131,12 +131,10 @@ PT_D void cw_set_space(CwState& st, v3 o, v3 d)
     st.oct_inv4 = oct * 0x01010101u;
 }
 
-// Byte j of w as a float: I2F.U8 (XU pipe, 60-66 % busy in wf_trace_cw). Measured alternatives, all slower
-// (profiles/r01_trace_kernel_history.md, r02_trace_kernel_history.md): the exact ALU+FMA form (PRMT builds
-// 2^23 + b, one FADD removes the 2^23: one more instruction per byte, +1.4-6 %); the same with the 2^23
-// folded into the slab offset (no extra instruction, boxes stored one cell larger because the folded offset
-// rounds to half a cell: +4-6 %, the ALU pipe takes the load and spills grow). The kernel is bound by issue
-// slots; the XU pipe is busy but not the limiter.
+// Byte j of w as a float: I2F.U8 on the XU pipe. Forms that were measured and lost (profiles/r01_ and
+// r02_trace_kernel_history.md): PRMT building 2^23 + b with a FADD to remove the 2^23 (one more instruction per
+// byte, +1.4-6 %); the 2^23 folded into the slab offset (the folded offset rounds to half a grid cell, so boxes
+// were stored one cell larger: +4-6 %). What is used next to it, for one axis of three, is the 2^15 form below.
 PT_D float u8f(uint32_t w, int j) { return (float)((w >> (8 * j)) & 0xFFu); }
 
 // Byte j of w as the float 32768 + b, built by ONE PRMT on the ALU pipe (no XU instruction): the byte lands in
@@ -145,7 +143,8 @@ PT_D float u8f(uint32_t w, int j) { return (float)((w >> (8 * j)) & 0xFFu); }
 // experiment costs 2^-9 of a grid cell in rounding instead of half a cell: no box padding. `magic` = 0x47000000
 // comes from the constant bank (Scene::cw_magic) so that PRMT takes the byte selector as its immediate.
 #ifndef CW_MAGIC
-#define CW_MAGIC 1      // bit mask of the axes converted this way: 1 x, 2 y, 4 z (measured: x alone is best)
+#define CW_MAGIC 1      // bit mask of the axes converted this way: 1 x, 2 y, 4 z. Measured at 36 warps/SM, where the XU
+                        // queue was what warps waited for (XU 69.5 % busy): x -2.2 %, x+y -0.8 %, all three +0.1 %
 #endif
 template<int AXIS, int J>
 PT_D float u8f_axis(uint32_t w, uint32_t magic)
