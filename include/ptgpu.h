@@ -247,6 +247,8 @@ int ptgpu_last_render_ms(ptgpu_ctx* ctx, float* ms, int32_t* launches);
  *              origin cell before every traversal launch; 0 = queue order.
  * "dyn_first": 1 (default) = with the flat scene a query enters the per-frame instances (the hero objects in
  *              front of the camera) before the static world; 0 = after.
+ * "l2_persist": percent (0..100, default 0) of the device's persisting-L2 maximum set aside for the compressed BVH nodes
+ *              through an access-policy window on the render stream (hits persist, everything else streams).
  * "plain_trace": 1 = every round, 2 = the primary round of the wavefront renderer is traced by the plain single-ray
  *              loop, one thread per ray, instead of the warp-scheduled kernel (reference point for measurements; default 0).
  * "top_smem":  1 = the traversal kernel stages the top levels of the flat BVH in shared memory (default 0:

@@ -134,6 +134,9 @@ struct ptgpu_ctx
     int sort = 1;                              // wavefront: bounce and shadow rays sorted by octant + origin cell
     int top_smem = 0;                          // wavefront: top levels of the flat BVH staged in shared memory
     int plain_trace = 0;                       // wavefront: 1 = every round, 2 = the primary round traced by the plain single-ray loop (reference point)
+    int l2_persist = 0;                        // percent of the persisting-L2 maximum set aside for the BVH nodes (0 = no access-policy window)
+    int l2_persist_applied = -1;               // what the render stream currently carries
+    size_t stat_l2_set_aside = 0, stat_l2_window = 0;
     int dyn_first = 1;                         // flat scene: per-frame instances are entered before the static world
 
     // static scene, reference layout
@@ -296,8 +299,46 @@ void wave_timing(ptgpu_ctx* ctx)
 #ifndef WF_SHADE_GRID
 #define WF_SHADE_GRID 8   // blocks per SM of the shade kernels (4 resident at 106 registers: two waves)
 #endif
+// L2 access-policy window over the compressed BVH nodes on the render stream: the traversal kernel's node loads
+// keep their lines as "persisting" while the 11.9 GB path-state pool streams through the same 126 MB L2
+// (option "l2_persist" = percent of cudaDevAttrMaxPersistingL2CacheSize to set aside; 0 = off).
+static void apply_l2_policy(ptgpu_ctx* ctx)
+{
+    if(ctx->l2_persist_applied == ctx->l2_persist) return;
+    ctx->l2_persist_applied = ctx->l2_persist;
+    int dev = 0, max_persist = 0, max_window = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
+    cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+    cudaStreamAttrValue attr;
+    memset(&attr, 0, sizeof(attr));
+    const size_t node_bytes = ctx->cwnodes.cap * sizeof(float4);
+    if(ctx->l2_persist <= 0 || max_persist <= 0 || max_window <= 0 || node_bytes == 0)
+    {
+        attr.accessPolicyWindow.num_bytes = 0;   // disables the window
+        cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &attr);
+        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 0);
+        cudaCtxResetPersistingL2Cache();
+        cudaGetLastError();
+        return;
+    }
+    const size_t set_aside = (size_t)max_persist / 100 * (size_t)ctx->l2_persist;
+    cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, set_aside);
+    // the flat scene's nodes are the tail of the array: the window covers the end if the array is larger than a window
+    const size_t win = node_bytes < (size_t)max_window ? node_bytes : (size_t)max_window;
+    attr.accessPolicyWindow.base_ptr = (char*)ctx->cwnodes.p + (node_bytes - win);
+    attr.accessPolicyWindow.num_bytes = win;
+    attr.accessPolicyWindow.hitRatio = set_aside >= win ? 1.0f : (float)((double)set_aside / (double)win);
+    attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &attr);
+    ctx->stat_l2_set_aside = set_aside; ctx->stat_l2_window = win;
+    cudaGetLastError();
+}
+
 int launch_wave(ptgpu_ctx* ctx, const Scene& sc, RenderJob job)
 {
+    apply_l2_policy(ctx);
     const int tiles_x = (job.w + WF_TILE - 1) / WF_TILE, tiles_y = (job.h + WF_TILE - 1) / WF_TILE;
     // slots per pixel: the largest power of two <= the sample count that keeps the pool in budget
     const size_t n_pix_padded = (size_t)tiles_x * tiles_y * WF_TILE * WF_TILE;
@@ -768,6 +809,7 @@ static int upload_static_common(
     ctx->have_static = true;
     ctx->have_frame = false;
     ctx->frame_on_device = false;
+    ctx->l2_persist_applied = -1;
     return 0;
 }
 
@@ -1188,6 +1230,7 @@ int ptgpu_set_option(ptgpu_ctx* ctx, const char* key, int64_t value)
         ctx->flat = (int)value; return 0; }
     if(!strcmp(key, "sort")) { if(value != 0 && value != 1) return fail(ctx, "sort must be 0 or 1"); ctx->sort = (int)value; return 0; }
     if(!strcmp(key, "dyn_first")) { if(value != 0 && value != 1) return fail(ctx, "dyn_first must be 0 or 1"); ctx->dyn_first = (int)value; return 0; }
+    if(!strcmp(key, "l2_persist")) { if(value < 0 || value > 100) return fail(ctx, "l2_persist is a percentage"); ctx->l2_persist = (int)value; return 0; }
     if(!strcmp(key, "plain_trace")) { if(value < 0 || value > 2) return fail(ctx, "plain_trace must be 0, 1 or 2"); ctx->plain_trace = (int)value; return 0; }
     if(!strcmp(key, "top_smem")) { if(value != 0 && value != 1) return fail(ctx, "top_smem must be 0 or 1"); ctx->top_smem = (int)value; return 0; }
     if(!strcmp(key, "lanes")) { if(value < 1 || value > 4096 || (value & (value - 1))) return fail(ctx, "lanes must be a power of two in 1..4096"); ctx->max_lanes = (int)value; return 0; }
@@ -1329,6 +1372,8 @@ int ptgpu_get_stat(ptgpu_ctx* ctx, const char* key, uint64_t* out)
     if(!strcmp(key, "trace_launches")) { wave_timing(ctx); *out = ctx->last_trace_launches; return 0; }
     if(!strcmp(key, "sort_us")) { wave_timing(ctx); *out = (uint64_t)(ctx->last_sort_us + 0.5); return 0; }
     if(!strcmp(key, "flat_tris")) { *out = ctx->have_flat ? ctx->flat_tris : 0; return 0; }
+    if(!strcmp(key, "l2_set_aside")) { *out = (double)ctx->stat_l2_set_aside; return 0; }
+    if(!strcmp(key, "l2_window")) { *out = (double)ctx->stat_l2_window; return 0; }
     if(!strcmp(key, "flat_nodes")) { *out = ctx->have_flat ? ctx->flat_nodes : 0; return 0; }
     if(!strcmp(key, "flat_depth")) { *out = ctx->have_flat ? ctx->flat_depth : 0; return 0; }
     if(!strcmp(key, "flat_build_ms")) { *out = ctx->have_flat ? (uint64_t)(1e3 * ctx->flat_build_seconds) : 0; return 0; }

@@ -21,7 +21,7 @@ import __graft_entry__ as ge  # noqa: E402
 
 
 # options a config does not name go back to these (options are sticky in a context)
-DEFAULTS = {"sort": 1, "dyn_first": 1, "top_smem": 0, "plain_trace": 0, "node_threshold": 16, "node_burst": -1, "tri_threshold": 8,
+DEFAULTS = {"sort": 1, "dyn_first": 1, "top_smem": 0, "plain_trace": 0, "l2_persist": 0, "node_threshold": 16, "node_burst": -1, "tri_threshold": 8,
             "xform_threshold": -1, "min_active": -1}
 
 
@@ -113,6 +113,8 @@ def main():
                     best = (ms, r.get_stat("trace_us") / 1e3, r.get_stat("sort_us") / 1e3, r.get_stat("shade_us") / 1e3)
             msg = "frame %4d %-28s %8.2f ms %7.1f Mpaths/s | trace %7.2f sort+gen %6.2f shade %6.2f" % (
                 (f, name, best[0], paths / best[0] / 1e3) + best[1:])
+            if c.get("l2_persist"):
+                msg += " | L2 set aside %.0f MB, window %.0f MB" % (r.get_stat("l2_set_aside") / 1e6, r.get_stat("l2_window") / 1e6)
             if args.check:
                 r.set_option("validate", 1)
                 r.render_rect(256, 148, 128, 64, 0, 16, 16)
