@@ -333,9 +333,8 @@ wf_generate_kernel(Scene sc, RenderJob job, WaveBuffers wb)
             wb.rng[slot] = make_uint4(seed.x, seed.y, seed.z, seed.w);
             wb.ray_o[slot] = make_float4(o.x, o.y, o.z, 0.0f);
             wb.ray_d[slot] = make_float4(d.x, d.y, d.z, -1.0f); // bsdf_pdf -1: MIS weight 1, |pdf| 1, no regularisation
-            wb.atten[slot] = make_float4(1, 1, 1, 1);
-            wb.contrib[slot] = make_float4(0, 0, 0, 0);
-            wb.nee[slot] = make_float4(0, 0, 0, 0);
+            // attenuation (1,1,1 | regularization 1), contribution 0 and "no NEE pending" are implied by bounce 0:
+            // the shade kernels do not read them for a camera ray (48 B written + 48 B read less per path)
             wb.cursor[slot] = make_int2(k, 0);
         }
         wf_append_block<8>(wb.q_trace + WF_SEG_PRIMARY * (size_t)wb.seg_cap, &wb.cnt->n_seg[WF_SEG_PRIMARY], ok, slot, s_tmp);
@@ -829,15 +828,16 @@ wf_shade_kernel(Scene sc, RenderJob job, WaveBuffers wb)
             const float4 fo = wb.ray_o[slot], fd = wb.ray_d[slot];
             v3 ray_o = mk3(fo.x, fo.y, fo.z), ray_d = mk3(fd.x, fd.y, fd.z);
             float bsdf_pdf = fd.w;
-            float4 fa = wb.atten[slot], fc = wb.contrib[slot];
+            int bounce = cursor.y;
+            // a camera ray (bounce 0) carries the initial path state implicitly (wf_generate does not write it)
+            float4 fa = make_float4(1, 1, 1, 1), fc = make_float4(0, 0, 0, 0), fn = make_float4(0, 0, 0, 0);
+            if(bounce > 0) { fa = wb.atten[slot]; fc = wb.contrib[slot]; fn = wb.nee[slot]; }
             v3 attenuation = mk3(fa.x, fa.y, fa.z), contribution = mk3(fc.x, fc.y, fc.z);
             float regularization = fa.w;
             const uint4 fs = wb.rng[slot];
             rng4 seed = {fs.x, fs.y, fs.z, fs.w};
-            int bounce = cursor.y;
 
             // NEE of the previous bounce (nee_branch tail, path_tracer.hh:611-619)
-            const float4 fn = wb.nee[slot];
             if(fn.w != 0.0f && wb.visible[slot] != 0u)
             {
                 const float4 sd = wb.shadow_d[slot];
@@ -854,9 +854,12 @@ wf_shade_kernel(Scene sc, RenderJob job, WaveBuffers wb)
             if(slot_ahead != WF_INVALID)
             {
                 prefetch_l2(wb.cursor + slot_ahead); prefetch_l2(wb.ray_o + slot_ahead); prefetch_l2(wb.ray_d + slot_ahead);
-                prefetch_l2(wb.atten + slot_ahead); prefetch_l2(wb.contrib + slot_ahead); prefetch_l2(wb.rng + slot_ahead);
-                prefetch_l2(wb.nee + slot_ahead); prefetch_l2(wb.hit + slot_ahead); prefetch_l2(wb.hit_prim + slot_ahead);
-                prefetch_l2(wb.visible + slot_ahead); prefetch_l2(wb.shadow_d + slot_ahead);
+                prefetch_l2(wb.rng + slot_ahead); prefetch_l2(wb.hit + slot_ahead); prefetch_l2(wb.hit_prim + slot_ahead);
+                if(bounce > 0)
+                {   // (camera rays do not read these; the next slot is almost always at this slot's bounce)
+                    prefetch_l2(wb.atten + slot_ahead); prefetch_l2(wb.contrib + slot_ahead); prefetch_l2(wb.nee + slot_ahead);
+                    prefetch_l2(wb.visible + slot_ahead); prefetch_l2(wb.shadow_d + slot_ahead);
+                }
             }
 #endif
 
